@@ -1,0 +1,45 @@
+// Compressed wide BVH (8-ary, quantised child boxes) — the layout that replaces the
+// reference's threaded binary BVH (reference src/main.rs:92-99, shader/scene.glsl:10-17,
+// 99-133).  The reference tree is one-primitive-per-leaf, walked in storage order; this one
+// is walked near-child-first with 16-byte vector loads.  POD shared by the host builder
+// (host/cwbvh_build.cpp) and the device traversal (device/traverse.cuh).
+#pragma once
+#include <stdint.h>
+
+namespace hjk {
+
+// 80-byte node = five 16-byte loads:
+//   q0: origin.xyz, {ex, ey, ez, imask}
+//   q1: child_base, prim_base, meta[0..3], meta[4..7]
+//   q2: qlo_x[0..7], qlo_y[0..7]      q3: qlo_z[0..7], qhi_x[0..7]      q4: qhi_y[0..7], qhi_z[0..7]
+// Child box i on axis a spans origin[a] + q{lo,hi}_a[i] * 2^(e[a]-127).
+// meta[i]: 0 = empty slot; inner child = 0b001'11sss (sss = slot, bit index 24+slot);
+//          leaf = (unary prim count 1/3/7) << 5 | first prim offset within the node (0..23).
+struct WideNode {
+  float origin[3];
+  uint8_t e[3];
+  uint8_t imask;  // bit s set = slot s holds an inner node
+  uint32_t child_base;
+  uint32_t prim_base;
+  uint8_t meta[8];
+  uint8_t qlo[3][8];
+  uint8_t qhi[3][8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be five 16-byte words");
+
+// 48-byte primitive record = three 16-byte loads.  The global shape id (reference index
+// space [spheres | quads | triangles], src/main.rs:233-243) rides in r0.w.
+//   triangle: r0 = (a.xyz, id)      r1 = (b-a, 0)        r2 = (c-a, 0)   (fp32 differences, as
+//             shapes/triangle.glsl:19-20 computes them per ray)
+//   sphere  : r0 = (centre.xyz, id) r1 = (radius, 0,0,0) r2 = 0
+//   quad    : r0 = (origin.xyz, id) r1 = (edge1, 0)      r2 = (edge2, 0)
+struct WidePrim {
+  float r0[4];
+  float r1[4];
+  float r2[4];
+};
+static_assert(sizeof(WidePrim) == 48, "WidePrim must be three 16-byte words");
+
+enum : uint32_t { kWideMaxLeafPrims = 3, kWideMaxNodePrims = 24 };
+
+}  // namespace hjk

@@ -1,0 +1,226 @@
+// Software traversal of the 8-wide compressed BVH (cwbvh.h) — replaces the node loop of
+// reference shader/scene.glsl:99-133 — and the primitive tests of shader/shapes/*.glsl,
+// restated with exact fp32 operation order so that accepted hits carry the same t/u/v bits
+// as the reference arithmetic.
+//
+// Closest hit keeps the reference's rule "after an accepted hit, tMax = t - M_EPS"
+// (scene.glsl:116), so primitives are accepted under the same interval test; only the
+// visiting order differs (near child first), which changes the winner only among hits
+// closer than M_EPS to each other (SURVEY §8-Q1 "ties").  Any hit returns as soon as one
+// primitive is accepted, which is exactly when the reference's shadow overload
+// (scene.glsl:92-96) returns true.
+//
+// Box culling uses FMA and conservative (outward-rounded, padded) boxes; it never decides a
+// hit, it only skips primitives whose exact test would fail.
+#pragma once
+#include "scene_dev.cuh"
+
+namespace hjk {
+
+HJK_HD int hi_bit(uint32_t v) {  // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)v);
+#else
+  return 31 - __builtin_clz(v);
+#endif
+}
+HJK_HD int pop_count(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+// per byte: 0xFF when the byte's top bit is set, else 0
+HJK_HD uint32_t sign_extend_s8x4(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r) : "r"(v));
+  return r;
+#else
+  return ((v >> 7) & 0x01010101u) * 0xFFu;
+#endif
+}
+HJK_HD float byte_to_float(uint32_t word, int j) { return (float)((word >> (8 * j)) & 0xFFu); }
+
+struct TravState {
+  float ox, oy, oz, dx, dy, dz, tmin, tmax;
+  float idx, idy, idz;   // reciprocal direction (zeros replaced by +-1e-20 before inversion)
+  uint32_t octinv4;      // (7 - octant) replicated in 4 bytes
+  uint32_t ng_x, ng_y;   // node group: first child index, (hit bits << 24) | imask
+  uint32_t tg_x, tg_y;   // primitive group: first record index, pending hit bits
+  int32_t hit_id;        // global shape id of the current winner, -1 = none
+  float hit_t, hit_u, hit_v;
+  uint32_t slot;         // caller payload (path slot / ray index)
+};
+
+HJK_HD float safe_rcp(float d) {
+  const float a = d < 0.f ? -d : d;
+  if (!(a > 1e-20f)) d = (x::as_uint(d) >> 31) ? -1e-20f : 1e-20f;
+  return 1.0f / d;
+}
+
+HJK_HD void trav_init(TravState& s, const f4& o_tmin, const f4& d_tmax) {
+  s.ox = o_tmin.x, s.oy = o_tmin.y, s.oz = o_tmin.z, s.tmin = o_tmin.w;
+  s.dx = d_tmax.x, s.dy = d_tmax.y, s.dz = d_tmax.z, s.tmax = d_tmax.w;
+  s.idx = safe_rcp(s.dx), s.idy = safe_rcp(s.dy), s.idz = safe_rcp(s.dz);
+  const uint32_t oct = (s.idx < 0.f ? 1u : 0u) | (s.idy < 0.f ? 2u : 0u) | (s.idz < 0.f ? 4u : 0u);
+  s.octinv4 = (7u - oct) * 0x01010101u;
+  s.ng_x = 0;
+  s.ng_y = 0x80000000u;  // "slot 7^octinv of a virtual parent with imask 0" = node 0
+  s.tg_x = s.tg_y = 0;
+  s.hit_id = -1;
+  s.hit_t = 0.f, s.hit_u = 0.f, s.hit_v = 0.f;
+}
+
+// 8 child boxes of one node against the ray interval; returns the 32-bit hit mask
+// (bits 31..24: inner children in near-to-far priority order, bits 23..0: primitives).
+HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, const f4& q2,
+                               const f4& q3, const f4& q4) {
+  const uint32_t e_imask = x::as_uint(q0.w);
+  const float adjx = x::as_float((e_imask & 0xFFu) << 23) * s.idx;
+  const float adjy = x::as_float(((e_imask >> 8) & 0xFFu) << 23) * s.idy;
+  const float adjz = x::as_float(((e_imask >> 16) & 0xFFu) << 23) * s.idz;
+  const float orgx = (q0.x - s.ox) * s.idx;
+  const float orgy = (q0.y - s.oy) * s.idy;
+  const float orgz = (q0.z - s.oz) * s.idz;
+  const bool nx = s.idx < 0.f, ny = s.idy < 0.f, nz = s.idz < 0.f;
+  uint32_t hitmask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int half = 0; half < 2; half++) {
+    const uint32_t meta4 = x::as_uint(half ? q1.w : q1.z);
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (s.octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t lox = x::as_uint(half ? q2.y : q2.x), loy = x::as_uint(half ? q2.w : q2.z);
+    const uint32_t loz = x::as_uint(half ? q3.y : q3.x), hix = x::as_uint(half ? q3.w : q3.z);
+    const uint32_t hiy = x::as_uint(half ? q4.y : q4.x), hiz = x::as_uint(half ? q4.w : q4.z);
+    const uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+    const uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+    const uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; j++) {
+      const float t0x = fmaf(byte_to_float(nearx, j), adjx, orgx);
+      const float t0y = fmaf(byte_to_float(neary, j), adjy, orgy);
+      const float t0z = fmaf(byte_to_float(nearz, j), adjz, orgz);
+      const float t1x = fmaf(byte_to_float(farx, j), adjx, orgx);
+      const float t1y = fmaf(byte_to_float(fary, j), adjy, orgy);
+      const float t1z = fmaf(byte_to_float(farz, j), adjz, orgz);
+      const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.tmin));
+      const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, s.tmax));
+      if (cmin <= cmax) {
+        const uint32_t bits = (child_bits4 >> (8 * j)) & 0xFFu;
+        const uint32_t index = (bit_index4 >> (8 * j)) & 0xFFu;
+        hitmask |= bits << index;
+      }
+    }
+  }
+  return hitmask;
+}
+
+// One primitive record against the ray, in the reference's exact arithmetic.
+//   triangle: shapes/triangle.glsl:15-52      sphere: shapes/sphere.glsl:18-41
+//   quad    : shapes/quad.glsl:7-25
+// On acceptance writes t (and u, v for triangles/quads) and returns true.
+HJK_HD bool intersect_prim(const SceneDev& sc, const TravState& s, const f4& r0, const f4& r1,
+                           const f4& r2, float& t_out, float& u_out, float& v_out) {
+  const uint32_t id = x::as_uint(r0.w);
+  const vec3 o = V3(s.ox, s.oy, s.oz), d = V3(s.dx, s.dy, s.dz);
+  if (id < sc.num_spheres) {
+    const float r = r1.x;
+    const vec3 l = o - xyz(r0);
+    const float b = x::mul(2.0f, dot(d, l));
+    const float c = x::sub(dot(l, l), x::mul(r, r));
+    float disc = x::sub(x::mul(b, b), x::mul(4.0f, c));
+    if (disc < 0.0f) return false;
+    disc = x::sqrt(disc);
+    const float t0 = x::mul(-0.5f, x::add(b, disc));
+    if (s.tmin <= t0 && t0 <= s.tmax) {
+      t_out = t0, u_out = 0.f, v_out = 0.f;
+      return true;
+    }
+    const float t1 = x::mul(-0.5f, x::sub(b, disc));
+    if (s.tmin <= t1 && t1 <= s.tmax) {
+      t_out = t1, u_out = 0.f, v_out = 0.f;
+      return true;
+    }
+    return false;
+  }
+  const vec3 e1 = xyz(r1), e2 = xyz(r2);
+  const vec3 n = cross(e1, e2);
+  const vec3 ro = o - xyz(r0);
+  const vec3 q = cross(ro, d);
+  const float dd = x::div(1.0f, dot(d, n));
+  if (id < sc.num_spheres + sc.num_quads) {
+    const float u = x::mul(dd, dot(-q, e2));
+    const float v = x::mul(dd, dot(q, e1));
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return false;
+    const float t = x::mul(dd, dot(-n, ro));
+    if (s.tmin <= t && t <= s.tmax) {
+      t_out = t, u_out = u, v_out = v;
+      return true;
+    }
+    return false;
+  }
+  const float u = x::mul(dd, dot(-q, e2));
+  const float v = x::mul(dd, dot(q, e1));
+  if (u < 0.f || v < 0.f || x::add(u, v) > 1.f) return false;
+  const float t = x::mul(dd, dot(-n, ro));
+  if (s.tmin <= t && t <= s.tmax) {
+    t_out = t, u_out = u, v_out = v;
+    return true;
+  }
+  return false;
+}
+
+// Runs the traversal until the ray is finished (returns true) or `yield()` asks to stop
+// (returns false; call again with the same state to resume).
+//   Stack: push(uint32_t, uint32_t), pop(uint32_t&, uint32_t&), empty().
+template <bool ANY_HIT, class Stack, class Yield>
+HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, Yield&& yield) {
+  for (;;) {
+    if (s.ng_y > 0x00FFFFFFu) {
+      const uint32_t hits_imask = s.ng_y;
+      const int bit = hi_bit(hits_imask);
+      s.ng_y &= ~(1u << bit);
+      if (s.ng_y > 0x00FFFFFFu) stack.push(s.ng_x, s.ng_y);
+      const uint32_t slot = ((uint32_t)bit - 24u) ^ (s.octinv4 & 0xFFu);
+      const uint32_t rel = (uint32_t)pop_count(hits_imask & ~(0xFFFFFFFFu << slot));
+      const f4* np = sc.nodes + (size_t)(s.ng_x + rel) * 5;
+      const f4 q0 = ld16(np), q1 = ld16(np + 1), q2 = ld16(np + 2), q3 = ld16(np + 3), q4 = ld16(np + 4);
+      const uint32_t hitmask = intersect_node(s, q0, q1, q2, q3, q4);
+      s.ng_x = x::as_uint(q1.x);
+      s.ng_y = (hitmask & 0xFF000000u) | (x::as_uint(q0.w) >> 24);
+      s.tg_x = x::as_uint(q1.y);
+      s.tg_y = hitmask & 0x00FFFFFFu;
+    } else {
+      s.tg_x = s.ng_x, s.tg_y = s.ng_y;
+      s.ng_x = s.ng_y = 0;
+    }
+    while (s.tg_y) {
+      const int i = hi_bit(s.tg_y);
+      s.tg_y &= ~(1u << i);
+      const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * 3;
+      const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
+      float t, u, v;
+      if (intersect_prim(sc, s, r0, r1, r2, t, u, v)) {
+        s.hit_id = (int32_t)x::as_uint(r0.w);
+        s.hit_t = t, s.hit_u = u, s.hit_v = v;
+        if (ANY_HIT) return true;
+        s.tmax = x::sub(t, eps);  // scene.glsl:116
+      }
+    }
+    if (s.ng_y <= 0x00FFFFFFu) {
+      if (stack.empty()) return true;
+      stack.pop(s.ng_x, s.ng_y);
+    }
+    if (yield()) return false;
+  }
+}
+
+}  // namespace hjk

@@ -1,0 +1,606 @@
+// Host builder of the 8-wide compressed BVH (cwbvh.h) that stands in for the reference's
+// `bvh::BVH::build` + flatten (reference src/main.rs:199-244).
+//
+//   1. per-primitive fp32 boxes (same Bounded rules as src/main.rs:69-82, src/shape.rs:13-20,
+//      46-53), inflated by an absolute pad so that the wide tree never culls a primitive the
+//      reference's exact-arithmetic test (shapes/triangle.glsl:15-52) would accept;
+//   2. binary BVH by binned SAH (16 bins, 3 axes), one primitive per leaf;
+//   3. SAH-optimal collapse of the binary tree into 8-wide nodes with <= 3 primitives per leaf
+//      (dynamic programme over "forest of at most i roots" costs, node cost 1, primitive 0.3);
+//   4. children assigned to slots so that slot ^ ray-octant gives a near-to-far order;
+//   5. child boxes quantised to 8 bits per plane, rounded outward, nodes emitted breadth-first
+//      (the children of a node are contiguous), primitives emitted in node order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "wide_bvh_host.h"
+
+namespace hjk {
+namespace {
+
+constexpr float kInf = std::numeric_limits<float>::infinity();
+constexpr float kNodeCost = 1.0f;
+constexpr float kPrimCost = 0.3f;
+constexpr int kBins = 16;
+
+struct Box {
+  float lo[3], hi[3];
+  void reset() {
+    for (int k = 0; k < 3; k++) {
+      lo[k] = kInf;
+      hi[k] = -kInf;
+    }
+  }
+  void grow(const Box& b) {
+    for (int k = 0; k < 3; k++) {
+      lo[k] = std::min(lo[k], b.lo[k]);
+      hi[k] = std::max(hi[k], b.hi[k]);
+    }
+  }
+  void grow(const float p[3]) {
+    for (int k = 0; k < 3; k++) {
+      lo[k] = std::min(lo[k], p[k]);
+      hi[k] = std::max(hi[k], p[k]);
+    }
+  }
+  float half_area() const {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    if (!(dx >= 0.f) || !(dy >= 0.f) || !(dz >= 0.f)) return 0.f;
+    return dx * dy + dy * dz + dz * dx;
+  }
+};
+
+struct Node2 {
+  Box box;
+  uint32_t left = 0, right = 0;  // children (inner)
+  uint32_t first = 0, count = 0; // range in the ordered primitive index array (count of the SUBTREE)
+  bool leaf = false;
+};
+
+struct Binary {
+  std::vector<Node2> nodes;
+  std::vector<uint32_t> order;  // primitive indices, subtree ranges are contiguous
+};
+
+void build_binary(const std::vector<Box>& boxes, Binary& out) {
+  const uint32_t n = (uint32_t)boxes.size();
+  out.order.resize(n);
+  for (uint32_t i = 0; i < n; i++) out.order[i] = i;
+  std::vector<float> cen((size_t)n * 3);
+  for (uint32_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) cen[(size_t)i * 3 + k] = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
+  out.nodes.clear();
+  out.nodes.reserve((size_t)2 * n);
+  out.nodes.emplace_back();
+  out.nodes[0].first = 0;
+  out.nodes[0].count = n;
+  std::vector<uint32_t> stack{0};
+  while (!stack.empty()) {
+    const uint32_t ni = stack.back();
+    stack.pop_back();
+    const uint32_t first = out.nodes[ni].first, count = out.nodes[ni].count;
+    uint32_t* idx = out.order.data() + first;
+    Box nb, cb;
+    nb.reset();
+    cb.reset();
+    for (uint32_t i = 0; i < count; i++) {
+      nb.grow(boxes[idx[i]]);
+      cb.grow(&cen[(size_t)idx[i] * 3]);
+    }
+    out.nodes[ni].box = nb;
+    if (count == 1) {
+      out.nodes[ni].leaf = true;
+      continue;
+    }
+    // binned SAH over the three axes
+    int best_axis = -1, best_split = -1;
+    float best_cost = kInf;
+    for (int axis = 0; axis < 3; axis++) {
+      const float c0 = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
+      if (!(ext > 0.f)) continue;
+      const float scale = (float)kBins / ext;
+      Box bb[kBins];
+      uint32_t bc[kBins];
+      for (int b = 0; b < kBins; b++) {
+        bb[b].reset();
+        bc[b] = 0;
+      }
+      for (uint32_t i = 0; i < count; i++) {
+        int b = (int)((cen[(size_t)idx[i] * 3 + axis] - c0) * scale);
+        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+        bb[b].grow(boxes[idx[i]]);
+        bc[b]++;
+      }
+      float right_area[kBins];
+      uint32_t right_cnt[kBins];
+      Box acc;
+      acc.reset();
+      uint32_t cnt = 0;
+      for (int b = kBins - 1; b > 0; b--) {
+        acc.grow(bb[b]);
+        cnt += bc[b];
+        right_area[b] = acc.half_area();
+        right_cnt[b] = cnt;
+      }
+      acc.reset();
+      cnt = 0;
+      for (int b = 0; b < kBins - 1; b++) {
+        acc.grow(bb[b]);
+        cnt += bc[b];
+        if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+        float cost = acc.half_area() * (float)cnt + right_area[b + 1] * (float)right_cnt[b + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = axis;
+          best_split = b;
+        }
+      }
+    }
+    uint32_t mid;
+    if (best_axis < 0) {
+      mid = count / 2;  // coincident centroids: split the list in half
+    } else {
+      const float c0 = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+      uint32_t* m = std::partition(idx, idx + count, [&](uint32_t p) {
+        int b = (int)((cen[(size_t)p * 3 + best_axis] - c0) * scale);
+        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+        return b <= best_split;
+      });
+      mid = (uint32_t)(m - idx);
+      if (mid == 0 || mid == count) mid = count / 2;
+    }
+    const uint32_t l = (uint32_t)out.nodes.size();
+    out.nodes.emplace_back();
+    out.nodes.emplace_back();
+    out.nodes[ni].left = l;
+    out.nodes[ni].right = l + 1;
+    out.nodes[l].first = first;
+    out.nodes[l].count = mid;
+    out.nodes[l + 1].first = first + mid;
+    out.nodes[l + 1].count = count - mid;
+    stack.push_back(l + 1);
+    stack.push_back(l);
+  }
+}
+
+// Dynamic programme of the wide-tree collapse.  cost[n][i-1] = cheapest way to represent the
+// subtree of binary node n as a forest of at most i wide-tree children (i = 1..7).
+struct Collapse {
+  std::vector<float> cost;      // 7 per node
+  std::vector<uint8_t> choice;  // 7 per node: i = 1: 0 leaf / 1 inner; i >= 2: k = roots given to
+                                // the left child, 0 = "same as i-1"
+  std::vector<uint8_t> root8;   // per node: left share when the node becomes an inner wide node
+};
+
+void collapse_costs(const Binary& bin, Collapse& c) {
+  const size_t n = bin.nodes.size();
+  c.cost.assign(n * 7, kInf);
+  c.choice.assign(n * 7, 0);
+  c.root8.assign(n, 0);
+  // children have larger indices than their parent (build order), so a reverse sweep is bottom-up
+  for (size_t ni = n; ni-- > 0;) {
+    const Node2& nd = bin.nodes[ni];
+    const float area = nd.box.half_area();
+    float* cn = &c.cost[ni * 7];
+    uint8_t* ch = &c.choice[ni * 7];
+    if (nd.leaf) {
+      for (int i = 0; i < 7; i++) {
+        cn[i] = area * kPrimCost;
+        ch[i] = 0;
+      }
+      continue;
+    }
+    const float* cl = &c.cost[(size_t)nd.left * 7];
+    const float* cr = &c.cost[(size_t)nd.right * 7];
+    auto distribute = [&](int j, uint8_t& kbest) {  // best split of j roots between the children
+      float best = kInf;
+      kbest = 1;
+      for (int k = 1; k < j; k++) {
+        float v = cl[k - 1] + cr[j - k - 1];
+        if (v < best) {
+          best = v;
+          kbest = (uint8_t)k;
+        }
+      }
+      return best;
+    };
+    uint8_t k8;
+    const float inner = distribute(8, k8) + area * kNodeCost;
+    c.root8[ni] = k8;
+    const float leaf = nd.count <= kWideMaxLeafPrims ? area * kPrimCost * (float)nd.count : kInf;
+    if (leaf <= inner) {
+      cn[0] = leaf;
+      ch[0] = 0;
+    } else {
+      cn[0] = inner;
+      ch[0] = 1;
+    }
+    for (int i = 2; i <= 7; i++) {
+      uint8_t k;
+      float d = distribute(i, k);
+      if (d < cn[i - 2]) {
+        cn[i - 1] = d;
+        ch[i - 1] = k;
+      } else {
+        cn[i - 1] = cn[i - 2];
+        ch[i - 1] = 0;
+      }
+    }
+  }
+}
+
+struct ChildRef {
+  uint32_t node2;  // binary node that becomes this wide child
+  bool leaf;
+};
+
+// expands "binary node n as a forest of at most i roots" into the list of wide children
+void gather_children(const Binary& bin, const Collapse& c, uint32_t n, int i, std::vector<ChildRef>& out) {
+  struct Item {
+    uint32_t n;
+    int i;
+  };
+  std::vector<Item> st{{n, i}};
+  while (!st.empty()) {
+    Item it = st.back();
+    st.pop_back();
+    const Node2& nd = bin.nodes[it.n];
+    if (nd.leaf) {
+      out.push_back({it.n, true});
+      continue;
+    }
+    int ii = it.i;
+    while (ii >= 2 && c.choice[(size_t)it.n * 7 + ii - 1] == 0) ii--;
+    if (ii == 1) {
+      out.push_back({it.n, c.choice[(size_t)it.n * 7] == 0});
+      continue;
+    }
+    const int k = c.choice[(size_t)it.n * 7 + ii - 1];
+    st.push_back({nd.right, ii - k});
+    st.push_back({nd.left, k});
+  }
+}
+
+void make_prim(const HjkScene& s, uint32_t shape, WidePrim& p) {
+  const uint32_t S = (uint32_t)s.spheres.count, Q = (uint32_t)s.quads.count;
+  std::memset(&p, 0, sizeof(p));
+  uint32_t id = shape;
+  if (shape < S) {
+    const HjkSphere& sp = ((const HjkSphere*)s.spheres.ptr)[shape];
+    for (int k = 0; k < 3; k++) p.r0[k] = sp.position[k];
+    p.r1[0] = sp.radius;
+  } else if (shape < S + Q) {
+    const HjkQuad& q = ((const HjkQuad*)s.quads.ptr)[shape - S];
+    for (int k = 0; k < 3; k++) {
+      p.r0[k] = q.origin[k];
+      p.r1[k] = q.edge1[k];
+      p.r2[k] = q.edge2[k];
+    }
+  } else {
+    const uint32_t* tri = (const uint32_t*)s.triangles.ptr + (size_t)3 * (shape - S - Q);
+    const HjkVertex* v = (const HjkVertex*)s.vertices.ptr;
+    for (int k = 0; k < 3; k++) {
+      // separately rounded fp32 differences, exactly what shapes/triangle.glsl:19-20 computes
+      volatile float ab = v[tri[1]].pos[k] - v[tri[0]].pos[k];
+      volatile float ac = v[tri[2]].pos[k] - v[tri[0]].pos[k];
+      p.r0[k] = v[tri[0]].pos[k];
+      p.r1[k] = ab;
+      p.r2[k] = ac;
+    }
+  }
+  std::memcpy(&p.r0[3], &id, 4);
+}
+
+Box shape_box(const HjkScene& s, uint32_t shape) {
+  const uint32_t S = (uint32_t)s.spheres.count, Q = (uint32_t)s.quads.count;
+  Box b;
+  b.reset();
+  if (shape < S) {
+    const HjkSphere& sp = ((const HjkSphere*)s.spheres.ptr)[shape];
+    const float r = std::fabs(sp.radius);
+    for (int k = 0; k < 3; k++) {
+      b.lo[k] = sp.position[k] - r;
+      b.hi[k] = sp.position[k] + r;
+    }
+  } else if (shape < S + Q) {
+    const HjkQuad& q = ((const HjkQuad*)s.quads.ptr)[shape - S];
+    float p[3];
+    b.grow(q.origin);
+    for (int k = 0; k < 3; k++) p[k] = q.origin[k] + q.edge1[k];
+    b.grow(p);
+    for (int k = 0; k < 3; k++) p[k] = q.origin[k] + q.edge2[k];
+    b.grow(p);
+    for (int k = 0; k < 3; k++) p[k] = q.origin[k] + q.edge1[k] + q.edge2[k];
+    b.grow(p);
+  } else {
+    const uint32_t* tri = (const uint32_t*)s.triangles.ptr + (size_t)3 * (shape - S - Q);
+    const HjkVertex* v = (const HjkVertex*)s.vertices.ptr;
+    for (int c = 0; c < 3; c++) b.grow(v[tri[c]].pos);
+  }
+  return b;
+}
+
+}  // namespace
+
+bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string& err) {
+  out = WideBvh();
+  const uint64_t S = s.spheres.count, Q = s.quads.count, T = s.triangles.count;
+  const uint64_t n64 = S + Q + T;
+  if (n64 == 0) {
+    err = "scene has no shapes";
+    return false;
+  }
+  if (n64 >= 0x7FFFFFFFull) {
+    err = "too many shapes for 31-bit shape ids";
+    return false;
+  }
+  const uint32_t n = (uint32_t)n64;
+  if (T) {
+    const uint32_t* tri = (const uint32_t*)s.triangles.ptr;
+    for (uint64_t i = 0; i < 3 * T; i++)
+      if (tri[i] >= s.vertices.count) {
+        err = "triangle vertex index out of range";
+        return false;
+      }
+  }
+  std::vector<Box> boxes(n);
+  Box scene;
+  scene.reset();
+  for (uint32_t i = 0; i < n; i++) {
+    boxes[i] = shape_box(s, i);
+    for (int k = 0; k < 3; k++)
+      if (!std::isfinite(boxes[i].lo[k]) || !std::isfinite(boxes[i].hi[k])) {
+        err = "non-finite shape bounds";
+        return false;
+      }
+    scene.grow(boxes[i]);
+  }
+  float ext = 0.f, mag = 0.f;
+  for (int k = 0; k < 3; k++) {
+    ext = std::max(ext, scene.hi[k] - scene.lo[k]);
+    mag = std::max(mag, std::max(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));
+  }
+  const float pad = pad_rel * std::max(ext, mag);
+  for (uint32_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) {
+      boxes[i].lo[k] -= pad;
+      boxes[i].hi[k] += pad;
+    }
+  for (int k = 0; k < 3; k++) {
+    out.scene_min[k] = scene.lo[k];
+    out.scene_max[k] = scene.hi[k];
+  }
+  out.pad = pad;
+
+  Binary bin;
+  build_binary(boxes, bin);
+  Collapse col;
+  collapse_costs(bin, col);
+  out.sah_cost = col.cost[0] / std::max(bin.nodes[0].box.half_area(), 1e-30f);
+
+  // breadth-first emission
+  struct Pending {
+    uint32_t node2;  // binary node whose subtree this wide node covers
+    uint32_t wide;   // index in out.nodes
+    uint32_t depth;
+  };
+  std::vector<Pending> queue;
+  out.nodes.emplace_back();
+  queue.push_back({0, 0, 1});
+  std::vector<ChildRef> kids;
+  for (size_t qi = 0; qi < queue.size(); qi++) {
+    const Pending cur = queue[qi];
+    out.depth = std::max(out.depth, cur.depth);
+    const Node2& nd = bin.nodes[cur.node2];
+    kids.clear();
+    if (nd.leaf) {
+      kids.push_back({cur.node2, true});  // single-primitive scene: root with one leaf child
+    } else {
+      const int k = col.root8[cur.node2];
+      gather_children(bin, col, nd.left, k, kids);
+      gather_children(bin, col, nd.right, 8 - k, kids);
+    }
+    const int nk = (int)kids.size();
+    // ---- slot assignment: greedy maximisation of sum dot(child centre - node centre, slot signs)
+    Box nb;
+    nb.reset();
+    for (int c = 0; c < nk; c++) nb.grow(bin.nodes[kids[c].node2].box);
+    float score[8][8];
+    for (int c = 0; c < nk; c++) {
+      const Box& cb = bin.nodes[kids[c].node2].box;
+      float d[3];
+      for (int k = 0; k < 3; k++) d[k] = 0.5f * (cb.lo[k] + cb.hi[k]) - 0.5f * (nb.lo[k] + nb.hi[k]);
+      for (int sl = 0; sl < 8; sl++)
+        score[c][sl] = ((sl & 1) ? d[0] : -d[0]) + ((sl & 2) ? d[1] : -d[1]) + ((sl & 4) ? d[2] : -d[2]);
+    }
+    int slot_of[8];
+    bool child_done[8] = {false}, slot_used[8] = {false};
+    for (int it = 0; it < nk; it++) {
+      int bc = -1, bs = -1;
+      float best = -kInf;
+      for (int c = 0; c < nk; c++) {
+        if (child_done[c]) continue;
+        for (int sl = 0; sl < 8; sl++) {
+          if (slot_used[sl]) continue;
+          if (score[c][sl] > best) {
+            best = score[c][sl];
+            bc = c;
+            bs = sl;
+          }
+        }
+      }
+      slot_of[bc] = bs;
+      child_done[bc] = true;
+      slot_used[bs] = true;
+    }
+    int child_in_slot[8];
+    for (int sl = 0; sl < 8; sl++) child_in_slot[sl] = -1;
+    for (int c = 0; c < nk; c++) child_in_slot[slot_of[c]] = c;
+
+    // ---- quantisation frame
+    WideNode wn;
+    std::memset(&wn, 0, sizeof(wn));
+    double scale[3];
+    for (int k = 0; k < 3; k++) {
+      wn.origin[k] = nb.lo[k];
+      const double extent = (double)nb.hi[k] - (double)nb.lo[k];
+      int e = extent > 0.0 ? (int)std::ceil(std::log2(extent / 255.0)) : -126;
+      e = std::max(e, -126);
+      while (std::ceil(extent / std::ldexp(1.0, e)) > 255.0) e++;
+      if (e > 127) {
+        err = "scene extent too large to quantise";
+        return false;
+      }
+      wn.e[k] = (uint8_t)(e + 127);
+      scale[k] = std::ldexp(1.0, e);
+    }
+    wn.child_base = (uint32_t)out.nodes.size();
+    wn.prim_base = (uint32_t)out.prims.size();
+    uint32_t prim_off = 0, n_inner = 0;
+    for (int sl = 0; sl < 8; sl++) {
+      const int c = child_in_slot[sl];
+      if (c < 0) {  // empty: inverted box never passes the slab test
+        for (int k = 0; k < 3; k++) {
+          wn.qlo[k][sl] = 255;
+          wn.qhi[k][sl] = 0;
+        }
+        continue;
+      }
+      const Node2& cn = bin.nodes[kids[c].node2];
+      for (int k = 0; k < 3; k++) {
+        double lo = std::floor(((double)cn.box.lo[k] - (double)wn.origin[k]) / scale[k]);
+        double hi = std::ceil(((double)cn.box.hi[k] - (double)wn.origin[k]) / scale[k]);
+        lo = std::min(std::max(lo, 0.0), 255.0);
+        hi = std::min(std::max(hi, 0.0), 255.0);
+        wn.qlo[k][sl] = (uint8_t)lo;
+        wn.qhi[k][sl] = (uint8_t)hi;
+      }
+      if (kids[c].leaf) {
+        const uint32_t cnt = cn.count;  // 1..3 primitives of this binary subtree
+        wn.meta[sl] = (uint8_t)((((1u << cnt) - 1u) << 5) | prim_off);
+        for (uint32_t i = 0; i < cnt; i++) {
+          WidePrim wp;
+          make_prim(s, bin.order[cn.first + i], wp);
+          out.prims.push_back(wp);
+        }
+        prim_off += cnt;
+      } else {
+        wn.meta[sl] = (uint8_t)((1u << 5) | (24u + (uint32_t)sl));
+        wn.imask |= (uint8_t)(1u << sl);
+        n_inner++;
+      }
+    }
+    // inner children are stored in slot order starting at child_base
+    for (int sl = 0; sl < 8; sl++) {
+      const int c = child_in_slot[sl];
+      if (c < 0 || kids[c].leaf) continue;
+      queue.push_back({kids[c].node2, (uint32_t)out.nodes.size(), cur.depth + 1});
+      out.nodes.emplace_back();
+    }
+    (void)n_inner;
+    out.nodes[cur.wide] = wn;
+  }
+  out.n_shapes = n;
+  return true;
+}
+
+// Structural check used by the not-gpu tests: every shape is referenced exactly once, every
+// child box (decoded the way the traversal decodes it) contains the boxes below it.
+bool validate_wide_bvh(const HjkScene& s, const WideBvh& bvh, std::string& err) {
+  const uint32_t n = bvh.n_shapes;
+  std::vector<uint8_t> seen(n, 0);
+  struct Item {
+    uint32_t node;
+    float lo[3], hi[3];
+    bool has_box;
+  };
+  std::vector<Item> st;
+  st.push_back({0, {0, 0, 0}, {0, 0, 0}, false});
+  uint64_t visited = 0;
+  while (!st.empty()) {
+    Item it = st.back();
+    st.pop_back();
+    if (it.node >= bvh.nodes.size()) {
+      err = "child index out of range";
+      return false;
+    }
+    visited++;
+    const WideNode& wn = bvh.nodes[it.node];
+    uint32_t inner_rank = 0;
+    for (int sl = 0; sl < 8; sl++) {
+      const uint8_t m = wn.meta[sl];
+      if (m == 0) continue;
+      float lo[3], hi[3];
+      for (int k = 0; k < 3; k++) {
+        const float sc = std::ldexp(1.0f, (int)wn.e[k] - 127);
+        lo[k] = wn.origin[k] + (float)wn.qlo[k][sl] * sc;
+        hi[k] = wn.origin[k] + (float)wn.qhi[k][sl] * sc;
+        if (it.has_box && (lo[k] < it.lo[k] - 1e-3f * std::fabs(it.lo[k]) - 1e-6f ||
+                           hi[k] > it.hi[k] + 1e-3f * std::fabs(it.hi[k]) + 1e-6f)) {
+          // a child may exceed its parent's QUANTISED box only by rounding; flag gross errors
+          const float tol = 2.f * sc + 1e-5f;
+          if (lo[k] < it.lo[k] - tol || hi[k] > it.hi[k] + tol) {
+            err = "child box escapes its parent";
+            return false;
+          }
+        }
+      }
+      const bool inner = (m & 0x18) == 0x18 && (m >> 5) == 1;
+      if (inner) {
+        if (!((wn.imask >> sl) & 1)) {
+          err = "imask disagrees with meta";
+          return false;
+        }
+        Item ch;
+        ch.node = wn.child_base + inner_rank++;
+        ch.has_box = true;
+        for (int k = 0; k < 3; k++) {
+          ch.lo[k] = lo[k];
+          ch.hi[k] = hi[k];
+        }
+        st.push_back(ch);
+      } else {
+        const uint32_t bits = m >> 5, off = m & 31u;
+        const uint32_t cnt = bits == 1 ? 1 : (bits == 3 ? 2 : (bits == 7 ? 3 : 0));
+        if (cnt == 0 || off + cnt > kWideMaxNodePrims) {
+          err = "bad leaf meta";
+          return false;
+        }
+        for (uint32_t i = 0; i < cnt; i++) {
+          const size_t pi = (size_t)wn.prim_base + off + i;
+          if (pi >= bvh.prims.size()) {
+            err = "primitive index out of range";
+            return false;
+          }
+          uint32_t id;
+          std::memcpy(&id, &bvh.prims[pi].r0[3], 4);
+          if (id >= n || seen[id]) {
+            err = "shape referenced twice or out of range";
+            return false;
+          }
+          seen[id] = 1;
+          Box b = shape_box(s, id);
+          for (int k = 0; k < 3; k++)
+            if (b.lo[k] < lo[k] || b.hi[k] > hi[k]) {
+              err = "leaf box does not contain its primitive";
+              return false;
+            }
+        }
+      }
+    }
+  }
+  for (uint32_t i = 0; i < n; i++)
+    if (!seen[i]) {
+      err = "shape missing from the tree";
+      return false;
+    }
+  if (visited != bvh.nodes.size()) {
+    err = "unreachable nodes";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace hjk

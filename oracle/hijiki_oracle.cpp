@@ -1,10 +1,11 @@
 // CPU ORACLE — TEST INFRASTRUCTURE ONLY (see hijiki_oracle.h).  PARITY UNPINNED by the
 // reference (no tests / fixtures upstream); pinned by SURVEY §8c known-answer vectors.
 //
-// Literal restatement of the reference GLSL.  Every function cites the shader lines it
+// Literal restatement of the reference GLSL; transcendentals per orc_math.h.  Every function cites the shader lines it
 // follows.  Build: g++ -O2 -ffp-contract=off -fno-fast-math (see Makefile) so that every
 // fp32 operation is a separate IEEE operation in source order.
 #include "hijiki_oracle.h"
+#include "orc_math.h"
 
 #include <atomic>
 #include <chrono>
@@ -40,7 +41,7 @@ inline vec3 normalize(vec3 a) {  // convention fixed by the oracle: v * inverses
   return a * inv;
 }
 inline vec3 reflect(vec3 I, vec3 N) { return I - 2.0f * dot(N, I) * N; }
-inline vec3 vexp(vec3 a) { return V(expf(a.x), expf(a.y), expf(a.z)); }
+inline vec3 vexp(vec3 a) { return V(orc_expf(a.x), orc_expf(a.y), orc_expf(a.z)); }
 inline float fract(float x) { return x - floorf(x); }
 inline float fminf_(float a, float b) { return a < b ? a : b; }  // GLSL min(x,y): y<x ? y : x
 inline float glsl_min(float x, float y) { return y < x ? y : x; }
@@ -156,8 +157,8 @@ struct Rng {
     float v = randUniformFloat();
     float r = sqrtf(u);
     float theta = (2.0f * M_PI_F) * v;
-    float x = r * cosf(theta);
-    float y = r * sinf(theta);
+    float x = r * orc_cosf(theta);
+    float y = r * orc_sinf(theta);
     return V(x, y, sqrtf(glsl_max(0.0f, 1.0f - u)));
   }
   vec3 randUniformSphere() {  // rand.glsl:32-40
@@ -166,7 +167,7 @@ struct Rng {
     float z = 2.0f * u - 1.0f;
     float theta = (2.0f * M_PI_F) * v;
     float r = sqrtf(1.0f - z * z);
-    return V(r * cosf(theta), r * sinf(theta), z);
+    return V(r * orc_cosf(theta), r * orc_sinf(theta), z);
   }
   vec3 randBarycentric() {  // rand.glsl:42-50 (the fold is kept as written)
     float u = randUniformFloat();
@@ -235,7 +236,7 @@ Ray getCameraRayAt(const Camera& c, float xx, float xy, float dimx, float dimy, 
   xx = xx - 0.5f * dimx;
   xy = xy - 0.5f * dimy;
   float radians = (0.5f * c.fov) * (M_PI_F / 180.0f);
-  float tn = tanf(radians);
+  float tn = orc_tanf(radians);
   xx = xx * tn / (0.5f * dimx);
   xy = xy * tn / (0.5f * dimx);
   Ray res;
@@ -345,8 +346,8 @@ void populateSphereIntersection(const Sphere& sphere, Intersection& its) {
   vec3 t = normalize(V(-n.z, 0.f, n.x));
   vec3 b = cross(n, t);
   its.frame = mat3{t, b, n};
-  its.uvx = 0.5f + atan2f(n.z, n.x) / (2.0f * M_PI_F);
-  its.uvy = 0.5f + asinf(glsl_min(glsl_max(n.y, -1.0f), 1.0f)) / M_PI_F;
+  its.uvx = 0.5f + orc_atan2f(n.z, n.x) / (2.0f * M_PI_F);
+  its.uvy = 0.5f + orc_asinf(glsl_min(glsl_max(n.y, -1.0f), 1.0f)) / M_PI_F;
   if (std::isnan(its.uvx)) its.uvx = 0.f;
 }
 
@@ -747,7 +748,7 @@ void reconstructBlock(const OrcBlock& blk, const OrcParams& p, SampleFn sample, 
                       int n_threads) {
   const int R = (int)p.recon_radius;
   const float gaussFac = -1.0f / (2.0f * p.recon_stddev * p.recon_stddev);
-  const float curveOffset = expf(gaussFac * (float)R * (float)R);
+  const float curveOffset = orc_expf(gaussFac * (float)R * (float)R);
   const uint32_t W = blk.original_dimension[0], H = blk.original_dimension[1];
   const uint32_t ext_x = blk.dimension[0] + 2 * R, ext_y = blk.dimension[1] + 2 * R;
   parallel_for(ext_y, n_threads, [&](uint64_t y0, uint64_t y1, int) {
@@ -767,7 +768,7 @@ void reconstructBlock(const OrcBlock& blk, const OrcParams& p, SampleFn sample, 
             if (localy + (uint32_t)dy >= blk.dimension[1]) continue;  // :39
             float sox = (float)dx + blk.sample_offset[0] - 0.5f;
             float soy = (float)dy + blk.sample_offset[1] - 0.5f;
-            float weight = expf(gaussFac * (sox * sox + soy * soy)) - curveOffset;  // :44
+            float weight = orc_expf(gaussFac * (sox * sox + soy * soy)) - curveOffset;  // :44
             if (weight < 0.f) continue;
             float cw[4], nd[4], al[4];
             int32_t sx = (int32_t)(localx + (uint32_t)dx), sy = (int32_t)(localy + (uint32_t)dy);
@@ -776,7 +777,7 @@ void reconstructBlock(const OrcBlock& blk, const OrcParams& p, SampleFn sample, 
             sample(2, sx, sy, al);
             vec3 nO = V(nd[0] - nc[0], nd[1] - nc[1], nd[2] - nc[2]);
             vec3 aO = V(al[0] - ac[0], al[1] - ac[1], al[2] - ac[2]);
-            weight *= expf(-(dot(nO, nO) * 2.0f + dot(aO, aO)));  // :54
+            weight *= orc_expf(-(dot(nO, nO) * 2.0f + dot(aO, aO)));  // :54
             float wv[4] = {weight * cw[0], weight * cw[1], weight * cw[2], weight * cw[3]};
             if (std::isnan(wv[0]) || std::isnan(wv[1]) || std::isnan(wv[2]) || std::isnan(wv[3])) continue;
             for (int k = 0; k < 4; k++) outv[k] += wv[k];
@@ -799,6 +800,19 @@ int default_threads(int n) {
 extern "C" {
 
 int orc_hardware_threads(void) { return default_threads(0); }
+
+void orc_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n) {
+  for (uint64_t i = 0; i < n; i++) {
+    switch (fn) {
+      case 0: out[i] = orc_sinf(a[i]); break;
+      case 1: out[i] = orc_cosf(a[i]); break;
+      case 2: out[i] = orc_tanf(a[i]); break;
+      case 3: out[i] = orc_expf(a[i]); break;
+      case 4: out[i] = orc_atan2f(a[i], b[i]); break;
+      default: out[i] = orc_asinf(a[i]); break;
+    }
+  }
+}
 
 uint32_t orc_seed_rng(uint32_t seed) {
   Rng r;
@@ -831,12 +845,12 @@ void orc_camera_ray(const void* scene_info64, float px, float py, float dim_x, f
 void orc_recon_spatial_weights(uint32_t radius, float stddev, float so_x, float so_y, float* out) {
   const int R = (int)radius;
   const float gaussFac = -1.0f / (2.0f * stddev * stddev);
-  const float curveOffset = expf(gaussFac * (float)R * (float)R);
+  const float curveOffset = orc_expf(gaussFac * (float)R * (float)R);
   int k = 0;
   for (int dx = -R; dx <= R; dx++)
     for (int dy = -R; dy <= R; dy++) {
       float sox = (float)dx + so_x - 0.5f, soy = (float)dy + so_y - 0.5f;
-      float w = expf(gaussFac * (sox * sox + soy * soy)) - curveOffset;
+      float w = orc_expf(gaussFac * (sox * sox + soy * soy)) - curveOffset;
       out[k++] = w < 0.f ? -1.f : w;
     }
 }

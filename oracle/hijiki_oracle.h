@@ -3,7 +3,7 @@
  *
  * TEST INFRASTRUCTURE ONLY.  This is a literal CPU restatement of the reference
  * shaders (reference shader/{rand,math,quaternion,block,render,scene,material,
- * reconstruction}.glsl, shader/shapes/*.glsl, shader/materials/*.glsl) used as the
+ * reconstruction}.glsl, shader/shapes/ and shader/materials/) used as the
  * checker for the CUDA path.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load it; the product (hijiki_b200/) never does.
  *
@@ -12,7 +12,9 @@
  * pinned only by the known-answer vectors derived from the reference arithmetic in
  * SURVEY.md §8c (tests/test_oracle_kat.py).  Floating-point conventions the GLSL spec
  * leaves open are fixed here: fp32 everywhere, no FMA contraction, IEEE div/sqrt,
- * libm transcendentals, normalize(v) = v * (1/sqrt(dot(v,v))).
+ * sin/cos/tan/exp/atan/asin = the fixed polynomial kernels specified in orc_math.h
+ * (<= 2 ulp from libm on the ranges the path uses, tests/test_math_spec.py),
+ * normalize(v) = v * (1/sqrt(dot(v,v))).
  */
 #ifndef HIJIKI_ORACLE_H
 #define HIJIKI_ORACLE_H
@@ -112,6 +114,9 @@ int orc_trace_path(const OrcScene* scene, const OrcBlock* block, uint32_t lx, ui
                    const OrcParams* params, OrcPathVertex* out, int capacity);
 
 int orc_hardware_threads(void);
+
+/* orc_math.h evaluated over an array (tests).  fn: 0 sin, 1 cos, 2 tan, 3 exp, 4 atan2(a,b), 5 asin */
+void orc_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,222 @@
+"""ctypes access to the two pieces of TEST infrastructure:
+
+* ``oracle/liboracle.so``           — CPU restatement of the reference shaders (the checker);
+* ``tests/native/libhjk_hosttest.so`` — the product's device headers compiled for the host, so
+  kernel logic can be checked in the CPU-only container.
+
+Neither is ever loaded by the product package ``hijiki_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+NATIVE_DIR = os.path.join(ROOT, "tests", "native")
+CBOX_OBJ = os.path.join(ROOT, "scenes", "cbox", "cbox.obj")
+
+import sys  # noqa: E402
+
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from hijiki_b200 import _abi  # noqa: E402  (struct layouts only; does not load the CUDA library)
+
+_P = C.c_void_p
+
+
+def _make(directory: str) -> None:
+    subprocess.run(["make", "-s", "-C", directory], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("max_bounces", C.c_uint32), ("rr_start", C.c_uint32), ("recon_radius", C.c_uint32),
+                ("recon_stddev", C.c_float), ("eps", C.c_float), ("use_bvh", C.c_uint32),
+                ("block_size", C.c_uint32), ("skip_recon", C.c_uint32)]
+
+
+class OrcStats(C.Structure):
+    _fields_ = [("n_paths", C.c_uint64), ("n_extension_rays", C.c_uint64), ("n_shadow_rays", C.c_uint64),
+                ("seconds", C.c_double)]
+
+
+class OrcPathVertex(C.Structure):
+    _fields_ = [("shape_id", C.c_int32), ("t", C.c_float), ("rng_after", C.c_uint32),
+                ("throughput", C.c_float * 3), ("total", C.c_float * 3), ("shadow_state", C.c_int32)]
+
+
+_oracle = None
+_hosttest = None
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        _make(ORACLE_DIR)
+        L = C.CDLL(os.path.join(ORACLE_DIR, "liboracle.so"))
+        L.orc_seed_rng.restype = C.c_uint32
+        L.orc_seed_rng.argtypes = [C.c_uint32]
+        L.orc_rand_uint.restype = C.c_uint32
+        L.orc_rand_uint.argtypes = [C.POINTER(C.c_uint32)]
+        L.orc_rand_uniform_float.restype = C.c_float
+        L.orc_rand_uniform_float.argtypes = [C.POINTER(C.c_uint32)]
+        L.orc_camera_ray.restype = None
+        L.orc_camera_ray.argtypes = [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]
+        L.orc_recon_spatial_weights.restype = None
+        L.orc_recon_spatial_weights.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, _P]
+        L.orc_trace.restype = C.c_int
+        L.orc_trace.argtypes = [C.POINTER(_abi.HjkScene), _P, C.c_uint64, C.c_int, C.c_float, _P, _P, _P, _P,
+                                C.c_int]
+        L.orc_occluded.restype = C.c_int
+        L.orc_occluded.argtypes = [C.POINTER(_abi.HjkScene), _P, C.c_uint64, C.c_int, C.c_float, _P, C.c_int]
+        L.orc_render.restype = C.c_int
+        L.orc_render.argtypes = [C.POINTER(_abi.HjkScene), _P, C.c_uint64, C.POINTER(OrcParams), _P,
+                                 C.POINTER(OrcStats), C.c_int]
+        L.orc_integrate_frame.restype = C.c_int
+        L.orc_integrate_frame.argtypes = [C.POINTER(_abi.HjkScene), _P, C.c_uint64, C.POINTER(OrcParams), _P,
+                                          C.POINTER(OrcStats), C.c_int]
+        L.orc_reconstruct_frame.restype = C.c_int
+        L.orc_reconstruct_frame.argtypes = [_P, C.c_uint64, C.POINTER(OrcParams), _P, _P, _P, _P, C.c_int]
+        L.orc_trace_path.restype = C.c_int
+        L.orc_trace_path.argtypes = [C.POINTER(_abi.HjkScene), _P, C.c_uint32, C.c_uint32,
+                                     C.POINTER(OrcParams), _P, C.c_int]
+        L.orc_hardware_threads.restype = C.c_int
+        L.orc_math_eval.restype = None
+        L.orc_math_eval.argtypes = [C.c_int, _P, _P, _P, C.c_uint64]
+        _oracle = L
+    return _oracle
+
+
+def hosttest() -> C.CDLL:
+    global _hosttest
+    if _hosttest is None:
+        _make(NATIVE_DIR)
+        L = C.CDLL(os.path.join(NATIVE_DIR, "libhjk_hosttest.so"))
+        L.ht_create.restype = _P
+        L.ht_create.argtypes = [C.POINTER(_abi.HjkScene), C.c_float, C.c_char_p, C.c_int]
+        L.ht_destroy.restype = None
+        L.ht_destroy.argtypes = [_P]
+        L.ht_bvh_stats.restype = None
+        L.ht_bvh_stats.argtypes = [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.ht_trace.restype = None
+        L.ht_trace.argtypes = [_P, _P, C.c_uint64, C.c_int, C.c_float, _P, _P, _P]
+        L.ht_render.restype = C.c_int
+        L.ht_render.argtypes = [_P, _P, C.c_uint64, C.POINTER(_abi.HjkParams), _P, _P, _P]
+        L.ht_denoise.restype = C.c_int
+        L.ht_denoise.argtypes = [_P, C.c_uint64, C.POINTER(_abi.HjkParams), _P, _P, _P, _P]
+        L.ht_math_eval.restype = None
+        L.ht_math_eval.argtypes = [C.c_int, _P, _P, _P, C.c_uint64]
+        # the harness links the host front-end sources too (scene loading without nvcc)
+        for name in ("hjk_host_scene_from_obj", "hjk_host_scene_terrain", "hjk_host_scene_spheres",
+                     "hjk_host_scene_view", "hjk_host_scene_free", "hjk_host_last_error",
+                     "hjk_host_generate_blocks", "hjk_host_write_exr"):
+            res, args = _abi._SIGNATURES[name]
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _hosttest = L
+    return _hosttest
+
+
+def ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def math_eval(lib_fn, fn: int, a, b=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = a if b is None else np.ascontiguousarray(b, dtype=np.float32)
+    out = np.empty_like(a)
+    lib_fn(fn, ptr(a), ptr(b), ptr(out), C.c_uint64(a.size))
+    return out
+
+
+class HostScene:
+    """A compiled scene produced by the host front-end (via whichever library `lib` is)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+        self.view = _abi.HjkScene()
+        rc = lib.hjk_host_scene_view(handle, C.byref(self.view))
+        assert rc == 0
+
+    @classmethod
+    def from_obj(cls, lib, path=CBOX_OBJ, put_spheres=False, with_bvh2=True):
+        h = _P()
+        rc = lib.hjk_host_scene_from_obj(path.encode(), int(put_spheres), int(with_bvh2), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(lib.hjk_host_last_error().decode())
+        return cls(lib, h)
+
+    @classmethod
+    def terrain(cls, lib, grid_n, seed=7, with_bvh2=True):
+        h = _P()
+        rc = lib.hjk_host_scene_terrain(grid_n, seed, int(with_bvh2), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(lib.hjk_host_last_error().decode())
+        return cls(lib, h)
+
+    @classmethod
+    def spheres(cls, lib, lattice_n, seed=7, with_bvh2=True):
+        h = _P()
+        rc = lib.hjk_host_scene_spheres(lattice_n, seed, int(with_bvh2), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(lib.hjk_host_last_error().decode())
+        return cls(lib, h)
+
+    def array(self, name: str) -> np.ndarray:
+        arr: _abi.HjkArray = getattr(self.view, name)
+        size, dtype, per = _abi.SCENE_ELEM[name]
+        if arr.count == 0 or not arr.ptr:
+            return np.zeros((0, per), dtype=dtype)
+        buf = (C.c_uint8 * (arr.count * size)).from_address(arr.ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(arr.count, per)
+
+    @property
+    def info(self) -> _abi.HjkSceneInfo:
+        return _abi.HjkSceneInfo.from_address(self.view.scene.ptr)
+
+    def close(self):
+        if self.handle:
+            self.lib.hjk_host_scene_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def generate_blocks(lib, width, height, spp, block_size=128, root_seed=0x48494A494B49) -> np.ndarray:
+    n = lib.hjk_host_generate_blocks(width, height, block_size, spp, root_seed, None, 0)
+    blocks = np.zeros(n, dtype=_abi.BLOCK_DTYPE)
+    lib.hjk_host_generate_blocks(width, height, block_size, spp, root_seed, ptr(blocks), n)
+    return blocks
+
+
+def camera_rays(scene: HostScene, width, height, offset=(0.5, 0.5), eps=1e-4) -> np.ndarray:
+    """Primary rays of every pixel, from the ORACLE's camera (render.glsl:26-36)."""
+    L = oracle()
+    rays = np.zeros(width * height, dtype=_abi.RAY_DTYPE)
+    one = np.zeros(1, dtype=_abi.RAY_DTYPE)
+    k = 0
+    for y in range(height):
+        for x in range(width):
+            L.orc_camera_ray(scene.view.scene.ptr, x + offset[0], y + offset[1], float(width), float(height),
+                             eps, ptr(one))
+            rays[k] = one[0]
+            k += 1
+    return rays
+
+
+def orc_params(max_bounces=1000, rr_start=3, radius=2, stddev=0.5, eps=1e-4, use_bvh=1, block_size=128,
+               skip_recon=0) -> OrcParams:
+    return OrcParams(max_bounces, rr_start, radius, stddev, eps, use_bvh, block_size, skip_recon)
+
+
+def hjk_params(max_bounces=1000, rr_start=3, radius=2, stddev=0.5, eps=1e-4, flags=0) -> _abi.HjkParams:
+    return _abi.HjkParams(max_bounces, rr_start, radius, stddev, eps, flags)

@@ -1,0 +1,292 @@
+// TEST HARNESS — compiles the DEVICE headers of the product (hijiki_b200/csrc/device/*.cuh)
+// for the host with g++ -ffp-contract=off, so that the traversal, shading and
+// reconstruction logic the CUDA kernels run can be unit-tested against the oracle in the
+// CPU-only container.  It is not part of libhijiki_b200 and is never shipped or timed: the
+// product has no CPU path.  The loops below replay the wavefront schedule of
+// csrc/device/kernels.cu sequentially (paths are independent, so order does not matter).
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../hijiki_b200/csrc/device/recon.cuh"
+#include "../../hijiki_b200/csrc/device/shade.cuh"
+#include "../../hijiki_b200/csrc/device/traverse.cuh"
+#include "../../hijiki_b200/csrc/host/pass_plan.h"
+#include "../../hijiki_b200/csrc/host/wide_bvh_host.h"
+
+using namespace hjk;
+
+namespace {
+
+struct HostStack {
+  uint32_t data[2 * 64];
+  int n = 0;
+  int max_n = 0;
+  void push(uint32_t a, uint32_t b) {
+    data[2 * n] = a, data[2 * n + 1] = b;
+    n++;
+    if (n > max_n) max_n = n;
+  }
+  void pop(uint32_t& a, uint32_t& b) {
+    n--;
+    a = data[2 * n], b = data[2 * n + 1];
+  }
+  bool empty() const { return n == 0; }
+};
+
+struct Harness {
+  WideBvh bvh;
+  SceneDev sc{};
+  std::vector<uint8_t> storage[12];
+  int max_stack = 0;
+};
+
+template <class T>
+const T* keep(std::vector<uint8_t>& store, const HjkArray& a, size_t elem) {
+  store.assign((const uint8_t*)a.ptr, (const uint8_t*)a.ptr + a.count * elem);
+  if (store.empty()) store.resize(16);
+  return (const T*)store.data();
+}
+
+struct FrameLayers {
+  const float* l0;
+  const float* l1;
+  const float* l2;
+  uint32_t W;
+  f4 at(const float* base, uint32_t gx, uint32_t gy) const {
+    const float* p = base + 4 * ((size_t)gy * W + gx);
+    return F4(p[0], p[1], p[2], p[3]);
+  }
+  f4 radiance(uint32_t gx, uint32_t gy) const { return at(l0, gx, gy); }
+  f4 feature(uint32_t gx, uint32_t gy) const { return at(l1, gx, gy); }
+  f4 albedo(uint32_t gx, uint32_t gy) const { return at(l2, gx, gy); }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* ht_create(const HjkScene* s, float pad_rel, char* err_out, int err_cap) {
+  Harness* h = new Harness();
+  std::string err;
+  if (!build_wide_bvh(*s, pad_rel, h->bvh, err) || !validate_wide_bvh(*s, h->bvh, err)) {
+    if (err_out && err_cap > 0) {
+      strncpy(err_out, err.c_str(), err_cap - 1);
+      err_out[err_cap - 1] = 0;
+    }
+    delete h;
+    return nullptr;
+  }
+  SceneDev& sc = h->sc;
+  sc.nodes = (const f4*)h->bvh.nodes.data();
+  sc.prims = (const f4*)h->bvh.prims.data();
+  const HjkSceneInfo* info = (const HjkSceneInfo*)s->scene.ptr;
+  sc.spheres = keep<f4>(h->storage[0], s->spheres, 16);
+  sc.quads = keep<f4>(h->storage[1], s->quads, 48);
+  sc.triangles = keep<uint32_t>(h->storage[2], s->triangles, 12);
+  sc.vertices = keep<f4>(h->storage[3], s->vertices, 32);
+  sc.materials = keep<uint32_t>(h->storage[4], s->materials, 4);
+  sc.emitters = keep<f4>(h->storage[5], s->emitters, 16);
+  sc.diffuse = keep<f4>(h->storage[6], s->diffuse, 16);
+  sc.diffusecb = keep<f4>(h->storage[7], s->diffusecb, 32);
+  sc.dielectric = keep<f4>(h->storage[8], s->dielectric, 16);
+  sc.emissive = keep<f4>(h->storage[9], s->emissive, 16);
+  sc.num_spheres = info->num_spheres;
+  sc.num_quads = info->num_quads;
+  sc.num_triangles = info->num_triangles;
+  sc.num_emitters = info->num_emitters;
+  sc.camera = info->camera;
+  return h;
+}
+void ht_destroy(void* p) { delete (Harness*)p; }
+
+void ht_bvh_stats(void* p, uint64_t* n_nodes, uint64_t* n_prims, uint32_t* depth, float* sah, float* pad,
+                  int* max_stack) {
+  Harness* h = (Harness*)p;
+  *n_nodes = h->bvh.nodes.size();
+  *n_prims = h->bvh.prims.size();
+  *depth = h->bvh.depth;
+  *sah = h->bvh.sah_cost;
+  *pad = h->bvh.pad;
+  *max_stack = h->max_stack;
+}
+
+// hjk_trace_first_hit semantics
+void ht_trace(void* p, const HjkRay* rays, uint64_t n, int any_hit, float eps, int32_t* shape_id,
+              float* t, float* uv) {
+  Harness* h = (Harness*)p;
+  for (uint64_t i = 0; i < n; i++) {
+    TravState s;
+    trav_init(s, F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min),
+              F4(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2], rays[i].t_max));
+    HostStack st;
+    auto never = []() { return false; };
+    if (any_hit) {
+      trav_run<true>(h->sc, s, st, eps, never);
+      shape_id[i] = s.hit_id >= 0 ? 1 : 0;
+    } else {
+      trav_run<false>(h->sc, s, st, eps, never);
+      shape_id[i] = s.hit_id;
+    }
+    if (st.max_n > h->max_stack) h->max_stack = st.max_n;
+    if (t) t[i] = s.hit_id >= 0 ? s.hit_t : 0.f;
+    if (uv) {
+      uv[2 * i] = s.hit_id >= 0 ? s.hit_u : 0.f;
+      uv[2 * i + 1] = s.hit_id >= 0 ? s.hit_v : 0.f;
+    }
+  }
+}
+
+// hjk_render semantics: integrates every pass into full-frame layers, then reconstructs it.
+// layers_out (optional): 3 x W*H float4 of the LAST pass.  counts: paths, extension, shadow.
+int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm,
+              float* accumulator, float* layers_out, uint64_t* counts) {
+  Harness* h = (Harness*)p;
+  PassPlan plan;
+  std::string err;
+  if (!plan_passes(blocks, n_blocks, plan, err)) return -1;
+  const uint32_t W = plan.width, H = plan.height;
+  const size_t npx = (size_t)W * H;
+  std::vector<float> layers(npx * 12, 0.f);
+  float* l0 = layers.data();
+  float* l1 = l0 + npx * 4;
+  float* l2 = l1 + npx * 4;
+  const int R = (int)prm->recon_radius, taps = 2 * R + 1;
+  std::vector<float> weights((size_t)n_blocks * taps * taps);
+  for (uint64_t b = 0; b < n_blocks; b++)
+    for (int dx = -R; dx <= R; dx++)
+      for (int dy = -R; dy <= R; dy++)
+        weights[b * taps * taps + (dx + R) * taps + (dy + R)] = recon_spatial_weight(
+            dx, dy, R, prm->recon_stddev, blocks[b].sample_offset[0], blocks[b].sample_offset[1]);
+  uint64_t n_paths = 0, n_ext = 0, n_sh = 0;
+  const size_t tiles = (size_t)plan.tiles_x * plan.tiles_y;
+  for (size_t pi = 0; pi < plan.passes.size(); pi++) {
+    const int32_t* tile_block = plan.tile_block.data() + pi * tiles;
+    std::fill(layers.begin(), layers.end(), 0.f);
+    for (uint32_t gy = 0; gy < H; gy++)
+      for (uint32_t gx = 0; gx < W; gx++) {
+        const int32_t b = tile_block[(size_t)(gy / plan.tile_h) * plan.tiles_x + gx / plan.tile_w];
+        if (b < 0) continue;
+        const HjkImageBlock& blk = blocks[b];
+        const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];
+        if (lx >= blk.dimension[0] || ly >= blk.dimension[1]) continue;
+        n_paths++;
+        // raygen (render.glsl:149-162)
+        VertexIn in;
+        in.rng = seed_rng(blk.seed + lx + ly * blk.dimension[0]);
+        camera_ray(h->sc.camera, x::add((float)gx, blk.sample_offset[0]),
+                   x::add((float)gy, blk.sample_offset[1]), (float)W, (float)H, prm->eps, in.ray_o, in.ray_d);
+        in.throughput = V3(1.f);
+        in.extinction = V3(0.f);
+        in.was_discrete = true;
+        float* r = l0 + 4 * ((size_t)gy * W + gx);
+        float* f = l1 + 4 * ((size_t)gy * W + gx);
+        r[0] = r[1] = r[2] = 0.f;
+        r[3] = 1.f;
+        for (uint32_t bounce = 0; bounce < prm->max_bounces; bounce++) {
+          in.bounce = bounce;
+          // extend
+          TravState s;
+          trav_init(s, in.ray_o, in.ray_d);
+          HostStack st;
+          auto never = []() { return false; };
+          n_ext++;
+          trav_run<false>(h->sc, s, st, prm->eps, never);
+          if (s.hit_id < 0) break;
+          in.hit_id = s.hit_id, in.hit_t = s.hit_t, in.hit_u = s.hit_u, in.hit_v = s.hit_v;
+          // shade
+          VertexOut o;
+          shade_vertex(h->sc, in, prm->max_bounces, prm->rr_start, prm->eps, o);
+          if (bounce == 0) f[0] = o.normal.x, f[1] = o.normal.y, f[2] = o.normal.z, f[3] = o.depth;
+          if (o.add_emission) {
+            r[0] = x::add(r[0], o.emission.x), r[1] = x::add(r[1], o.emission.y), r[2] = x::add(r[2], o.emission.z);
+          }
+          // shadow
+          if (o.has_shadow) {
+            n_sh++;
+            TravState ss;
+            trav_init(ss, o.sh_o, o.sh_d);
+            HostStack st2;
+            trav_run<true>(h->sc, ss, st2, prm->eps, never);
+            if (ss.hit_id < 0) {
+              r[0] = x::add(r[0], o.contribution.x), r[1] = x::add(r[1], o.contribution.y),
+              r[2] = x::add(r[2], o.contribution.z);
+            }
+          }
+          if (!o.continues) break;
+          in.ray_o = o.next_o, in.ray_d = o.next_d;
+          in.throughput = o.throughput, in.extinction = o.extinction;
+          in.rng = o.rng, in.was_discrete = o.was_discrete;
+        }
+      }
+    if (!(prm->flags & HJK_RENDER_NO_RECON)) {
+      PassDev ps;
+      ps.width = W, ps.height = H, ps.tile_w = plan.tile_w, ps.tile_h = plan.tile_h;
+      ps.tiles_x = plan.tiles_x, ps.tiles_y = plan.tiles_y;
+      ps.tile_block = tile_block;
+      ps.blocks = blocks;
+      ps.weights = weights.data();
+      ps.radius = R;
+      FrameLayers L{l0, l1, l2, W};
+      for (uint32_t gy = 0; gy < H; gy++)
+        for (uint32_t gx = 0; gx < W; gx++) {
+          float* a = accumulator + 4 * ((size_t)gy * W + gx);
+          f4 v = reconstruct_pixel<false>(ps, L, gx, gy, F4(a[0], a[1], a[2], a[3]));
+          a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
+        }
+    }
+  }
+  if (layers_out) memcpy(layers_out, layers.data(), layers.size() * 4);
+  if (counts) counts[0] = n_paths, counts[1] = n_ext, counts[2] = n_sh;
+  return 0;
+}
+
+// reconstruction of caller-supplied layers (hjk_denoise_pass semantics)
+int ht_denoise(const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm, const float* radiance,
+               const float* normal_depth, const float* albedo, float* accumulator) {
+  PassPlan plan;
+  std::string err;
+  if (!plan_passes(blocks, n_blocks, plan, err)) return -1;
+  const int R = (int)prm->recon_radius, taps = 2 * R + 1;
+  std::vector<float> weights((size_t)n_blocks * taps * taps);
+  for (uint64_t b = 0; b < n_blocks; b++)
+    for (int dx = -R; dx <= R; dx++)
+      for (int dy = -R; dy <= R; dy++)
+        weights[b * taps * taps + (dx + R) * taps + (dy + R)] = recon_spatial_weight(
+            dx, dy, R, prm->recon_stddev, blocks[b].sample_offset[0], blocks[b].sample_offset[1]);
+  const size_t tiles = (size_t)plan.tiles_x * plan.tiles_y;
+  for (size_t pi = 0; pi < plan.passes.size(); pi++) {
+    PassDev ps;
+    ps.width = plan.width, ps.height = plan.height, ps.tile_w = plan.tile_w, ps.tile_h = plan.tile_h;
+    ps.tiles_x = plan.tiles_x, ps.tiles_y = plan.tiles_y;
+    ps.tile_block = plan.tile_block.data() + pi * tiles;
+    ps.blocks = blocks;
+    ps.weights = weights.data();
+    ps.radius = R;
+    FrameLayers L{radiance, normal_depth, albedo, plan.width};
+    for (uint32_t gy = 0; gy < plan.height; gy++)
+      for (uint32_t gx = 0; gx < plan.width; gx++) {
+        float* a = accumulator + 4 * ((size_t)gy * plan.width + gx);
+        f4 v = albedo ? reconstruct_pixel<true>(ps, L, gx, gy, F4(a[0], a[1], a[2], a[3]))
+                      : reconstruct_pixel<false>(ps, L, gx, gy, F4(a[0], a[1], a[2], a[3]));
+        a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
+      }
+  }
+  return 0;
+}
+
+// hjk_math.cuh evaluated on the host (compared bit-for-bit with oracle/orc_math.h)
+void ht_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n) {
+  for (uint64_t i = 0; i < n; i++) {
+    switch (fn) {
+      case 0: out[i] = sin_det(a[i]); break;
+      case 1: out[i] = cos_det(a[i]); break;
+      case 2: out[i] = tan_det(a[i]); break;
+      case 3: out[i] = exp_det(a[i]); break;
+      case 4: out[i] = atan2_det(a[i], b[i]); break;
+      default: out[i] = asin_det(a[i]); break;
+    }
+  }
+}
+
+}  // extern "C"
