@@ -109,6 +109,7 @@ _SIGNATURES = {
     "hjk_allreduce_accumulator": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "hjk_accumulator_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hjk_synchronize": (C.c_int, [_P]),
+    "hjk_set_stream": (C.c_int, [_P, _P]),
     "hjk_set_profiling": (C.c_int, [_P, C.c_int]),
     "hjk_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "hjk_get_info": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
@@ -122,7 +123,7 @@ _SIGNATURES = {
     "hjk_host_generate_blocks": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                               _P, C.c_uint64]),
     "hjk_host_write_exr": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32, C.c_uint64]),
-    "hjk_host_bvh_stats": (C.c_int, [C.POINTER(HjkScene), C.c_float, C.POINTER(C.c_uint64)]),
+    "hjk_host_bvh_stats": (C.c_int, [C.POINTER(HjkScene), C.c_float, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

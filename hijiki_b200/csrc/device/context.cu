@@ -1,0 +1,889 @@
+// C ABI of the device side (include/hijiki_b200.h): context, scene upload, the wavefront
+// render loop that replaces Renderer::render (reference src/main.rs:1316-1355), readback,
+// the parity hook and the standalone reconstruction entry.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../host/pass_plan.h"
+#include "../host/wide_bvh_host.h"
+#include "kernels.cuh"
+
+using namespace hjk;
+
+namespace {
+
+// ------------------------------------------------------------------ NCCL via dlopen
+// The library has no link-time dependency on NCCL; multi-GPU hosts that do not bring their
+// own communicator (see hjk_accumulator_device_ptr) get one through these entry points.
+struct Id128 {  // ncclUniqueId, passed by value
+  char bytes[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl(std::string& err) {
+  if (g_nccl.handle) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    err = "cannot dlopen libnccl.so.2";
+    return false;
+  }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    err = "libnccl is missing expected symbols";
+    return false;
+  }
+  g_nccl.handle = h;
+  return true;
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count) {  // grow-only
+    if (count <= n) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct HjkContext {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk[2] = {nullptr, nullptr};
+  int n_sms = 0;
+  int blocks_trav = 0, blocks_tile = 0;  // resident CTAs per SM of the persistent kernels
+  std::string error;
+  bool profiling = false;
+  uint64_t wave_paths = 4u << 20;  // target camera paths per wave
+  float bvh_pad_rel = kDefaultBvhPadRel;
+
+  // scene
+  bool has_scene = false;
+  SceneDev scene{};
+  bool has_extinction = false;
+  WideBvh bvh_host_stats;  // nodes/prims cleared after upload; keeps depth etc.
+  uint64_t n_nodes = 0, n_prims = 0;
+  DevBuf<f4> d_nodes, d_prims, d_spheres, d_quads, d_vertices, d_emitters, d_diffuse, d_diffusecb,
+      d_dielectric, d_emissive;
+  DevBuf<uint32_t> d_triangles, d_materials;
+
+  // frame
+  uint32_t width = 0, height = 0;
+  DevBuf<f4> d_acc, d_norm;
+
+  // wave buffers
+  DevBuf<f4> d_ray_o, d_ray_d, d_hit, d_thr, d_ext, d_layer0, d_layer1, d_sh_o, d_sh_d, d_sh_c;
+  DevBuf<uint32_t> d_ext_q0, d_ext_q1, d_tag_q, d_counters;
+  DevBuf<int32_t> d_tile_block;
+  DevBuf<HjkImageBlock> d_blocks;
+  DevBuf<float> d_weights;
+  std::vector<uint32_t> h_counters;
+  uint32_t last_wave_passes = 0;  // for hjk_read_intermediate
+  bool have_features = false;
+
+  // resident block lists
+  struct Resident {
+    std::vector<HjkImageBlock> host;
+    HjkImageBlock* dev = nullptr;
+  };
+  std::map<uint64_t, Resident> resident;
+  uint64_t next_handle = 1;
+
+  // standalone denoise
+  DevBuf<f4> d_dn0, d_dn1, d_dn2;
+  std::vector<HjkImageBlock> dn_blocks;
+  bool dn_has_albedo = false;
+
+  // NCCL
+  void* comm = nullptr;
+  int rank = 0, n_ranks = 1;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    error = buf;
+    return code;
+  }
+};
+
+#define HJK_CUDA(ctx, call)                                                                    \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return (ctx)->fail(e_ == cudaErrorMemoryAllocation ? HJK_ERR_OUT_OF_MEMORY : HJK_ERR_CUDA, \
+                         "%s failed: %s", #call, cudaGetErrorString(e_));                      \
+  } while (0)
+
+namespace {
+
+template <class T>
+int upload(HjkContext* c, DevBuf<T>& buf, const HjkArray& a, size_t elem_bytes) {
+  const size_t bytes = (size_t)a.count * elem_bytes;
+  const size_t n = (bytes + sizeof(T) - 1) / sizeof(T);
+  HJK_CUDA(c, buf.ensure(std::max<size_t>(n, 1)));
+  if (bytes) {
+    if (!a.ptr) return c->fail(HJK_ERR_INVALID_ARGUMENT, "scene array has a count but no pointer");
+    HJK_CUDA(c, cudaMemcpyAsync(buf.p, a.ptr, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  return HJK_OK;
+}
+
+int grid_for(const HjkContext* c, int per_sm) { return c->n_sms * std::max(per_sm, 1); }
+
+struct KernelTimer {  // per-stage CUDA-event timing, only when profiling is on
+  HjkContext* c;
+  HjkStats* st;
+  int slot;
+  KernelTimer(HjkContext* c_, HjkStats* st_, int slot_) : c(c_), st(st_), slot(slot_) {
+    if (c->profiling && st) cudaEventRecord(c->evk[0], c->stream);
+  }
+  ~KernelTimer() {
+    if (c->profiling && st) {
+      cudaEventRecord(c->evk[1], c->stream);
+      cudaEventSynchronize(c->evk[1]);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
+      st->kernel_ms[slot] += ms;
+    }
+  }
+};
+
+int ensure_frame(HjkContext* c, uint32_t w, uint32_t h, bool zero) {
+  const size_t n = (size_t)w * h;
+  const bool fresh = c->width != w || c->height != h || !c->d_acc.p;
+  HJK_CUDA(c, c->d_acc.ensure(n));
+  c->width = w;
+  c->height = h;
+  if (fresh || zero) HJK_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, n * sizeof(f4), c->stream));
+  return HJK_OK;
+}
+
+int launch_recon(HjkContext* c, const PassDev& ps, uint32_t n_passes, const f4* l0, const f4* l1, const f4* l2,
+                 f4* acc) {
+  if (ps.radius < 0 || ps.radius > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
+  const int pitch = kReconTileX + 2 * ps.radius, rows = kReconTileY + 2 * ps.radius;
+  const size_t smem = (size_t)pitch * rows * sizeof(f4) * (l2 ? 3 : 2);
+  dim3 block(kReconTileX, kReconTileY);
+  dim3 grid((ps.width + kReconTileX - 1) / kReconTileX, (ps.height + kReconTileY - 1) / kReconTileY);
+  if (l2) {
+    if (smem > 48 * 1024)
+      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_recon<true><<<grid, block, smem, c->stream>>>(ps, n_passes, l0, l1, l2, acc);
+  } else {
+    if (smem > 48 * 1024)
+      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_recon<false><<<grid, block, smem, c->stream>>>(ps, n_passes, l0, l1, nullptr, acc);
+  }
+  HJK_CUDA(c, cudaGetLastError());
+  return HJK_OK;
+}
+
+// The render loop over a block list that already lives on the device (d_blocks) and on the
+// host (blocks).  Replaces Renderer::render, src/main.rs:1316-1355.
+int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBlock* d_blocks, uint64_t n_blocks,
+                  const HjkParams* prm, HjkStats* stats) {
+  if (!c->has_scene) return c->fail(HJK_ERR_NO_SCENE, "hjk_render before hjk_scene_upload");
+  if (!prm) return c->fail(HJK_ERR_INVALID_ARGUMENT, "params is null");
+  if (prm->max_bounces == 0 || prm->max_bounces > (1u << 16))
+    return c->fail(HJK_ERR_UNSUPPORTED, "max_bounces must be in [1, 65536]");
+  if (!(prm->recon_stddev > 0.f)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "recon_stddev must be positive");
+  PassPlan plan;
+  std::string err;
+  if (!plan_passes(blocks, n_blocks, plan, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+  if (c->width && (c->width != plan.width || c->height != plan.height) && c->d_acc.p)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "blocks are for a %ux%u image but the frame is %ux%u", plan.width,
+                   plan.height, c->width, c->height);
+  int rc = ensure_frame(c, plan.width, plan.height, false);
+  if (rc) return rc;
+
+  const size_t n_pixels = (size_t)plan.width * plan.height;
+  const size_t tiles = (size_t)plan.tiles_x * plan.tiles_y;
+  const uint32_t n_passes = (uint32_t)plan.passes.size();
+  uint32_t wave_passes = (uint32_t)std::max<uint64_t>(1, (c->wave_paths + n_pixels / 2) / n_pixels);
+  wave_passes = std::min(wave_passes, n_passes);
+  const size_t n_slots = n_pixels * wave_passes;
+  if (n_slots > 0x7FFFFFFFull) return c->fail(HJK_ERR_UNSUPPORTED, "wave too large");
+  const int R = (int)prm->recon_radius, taps = 2 * R + 1;
+  const bool do_recon = !(prm->flags & HJK_RENDER_NO_RECON);
+  if (do_recon && R > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
+
+  HJK_CUDA(c, c->d_ray_o.ensure(n_slots));
+  HJK_CUDA(c, c->d_ray_d.ensure(n_slots));
+  HJK_CUDA(c, c->d_hit.ensure(n_slots));
+  HJK_CUDA(c, c->d_thr.ensure(n_slots));
+  if (c->has_extinction) HJK_CUDA(c, c->d_ext.ensure(n_slots));
+  HJK_CUDA(c, c->d_layer0.ensure(n_slots));
+  HJK_CUDA(c, c->d_layer1.ensure(n_slots));
+  HJK_CUDA(c, c->d_sh_o.ensure(n_slots));
+  HJK_CUDA(c, c->d_sh_d.ensure(n_slots));
+  HJK_CUDA(c, c->d_sh_c.ensure(n_slots));
+  HJK_CUDA(c, c->d_ext_q0.ensure(n_slots));
+  HJK_CUDA(c, c->d_ext_q1.ensure(n_slots));
+  HJK_CUDA(c, c->d_tag_q.ensure(n_slots * 5));
+  const size_t n_ctr = ((size_t)prm->max_bounces + 1) * CTR_STRIDE;
+  HJK_CUDA(c, c->d_counters.ensure(n_ctr));
+  HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
+  HJK_CUDA(c, c->d_weights.ensure((size_t)n_blocks * taps * taps));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_tile_block.p, plan.tile_block.data(), plan.tile_block.size() * 4,
+                              cudaMemcpyHostToDevice, c->stream));
+
+  HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  uint64_t launches = 0;
+  if (stats) {
+    const float keep_ms = 0.f;
+    (void)keep_ms;
+    memset(stats, 0, sizeof(*stats));
+  }
+  if (do_recon) {
+    KernelTimer t(c, stats, HJK_K_OTHER);
+    k_recon_weights<<<std::max<int>(1, (int)std::min<size_t>(1024, ((size_t)n_blocks * taps * taps + 255) / 256)), 256,
+                      0, c->stream>>>(d_blocks, (uint32_t)n_blocks, R, prm->recon_stddev, c->d_weights.p);
+    launches++;
+  }
+
+  WaveDev w{};
+  w.scene = c->scene;
+  w.width = plan.width, w.height = plan.height, w.n_pixels = (uint32_t)n_pixels;
+  w.tile_w = plan.tile_w, w.tile_h = plan.tile_h, w.tiles_x = plan.tiles_x, w.tiles_y = plan.tiles_y;
+  w.blocks = d_blocks;
+  w.weights = c->d_weights.p;
+  w.ray_o = c->d_ray_o.p, w.ray_d = c->d_ray_d.p, w.hit = c->d_hit.p, w.thr_rng = c->d_thr.p;
+  w.extinction = c->d_ext.p;
+  w.layer0 = c->d_layer0.p, w.layer1 = c->d_layer1.p;
+  w.ext_q[0] = c->d_ext_q0.p, w.ext_q[1] = c->d_ext_q1.p, w.tag_q = c->d_tag_q.p;
+  w.sh_o = c->d_sh_o.p, w.sh_d = c->d_sh_d.p, w.sh_c = c->d_sh_c.p;
+  w.counters = c->d_counters.p;
+  w.accumulator = c->d_acc.p;
+  w.max_bounces = prm->max_bounces, w.rr_start = prm->rr_start;
+  w.recon_radius = R;
+  w.eps = prm->eps;
+  w.has_extinction = c->has_extinction ? 1u : 0u;
+
+  const int g_trav = grid_for(c, c->blocks_trav), g_tile = grid_for(c, c->blocks_tile);
+  uint64_t n_ext = 0, n_sh = 0, n_paths = 0;
+  c->h_counters.resize(n_ctr);
+  // with the reference's bounce limit (1000) paths die by roulette long before the limit:
+  // look at the live count every `check_every` bounces and stop when the wave is empty
+  const uint32_t check_every = 8;
+
+  for (uint32_t p0 = 0; p0 < n_passes; p0 += wave_passes) {
+    const uint32_t wp = std::min(wave_passes, n_passes - p0);
+    w.n_wave_passes = wp;
+    w.n_slots = (uint32_t)(n_pixels * wp);
+    w.tile_block = c->d_tile_block.p + (size_t)p0 * tiles;
+    HJK_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, n_ctr * 4, c->stream));
+    {
+      KernelTimer t(c, stats, HJK_K_RAYGEN);
+      k_raygen<<<g_tile, kTileThreads, 0, c->stream>>>(w);
+      launches++;
+    }
+    uint32_t bounces_run = 0;
+    for (uint32_t b = 0; b < prm->max_bounces; b++) {
+      {
+        KernelTimer t(c, stats, HJK_K_EXTEND);
+        k_extend<<<g_trav, kTravThreads, 0, c->stream>>>(w, b);
+      }
+      {
+        KernelTimer t(c, stats, HJK_K_SORT);
+        k_bin<<<g_tile, kTileThreads, 0, c->stream>>>(w, b);
+      }
+      {
+        KernelTimer t(c, stats, HJK_K_SHADE);
+        k_shade<<<g_tile, kTileThreads, 0, c->stream>>>(w, b);
+      }
+      {
+        KernelTimer t(c, stats, HJK_K_SHADOW);
+        k_shadow<<<g_trav, kTravThreads, 0, c->stream>>>(w, b);
+      }
+      launches += 4;
+      bounces_run = b + 1;
+      if (b + 1 < prm->max_bounces && (b + 1) % check_every == 0) {
+        uint32_t live = 0;
+        HJK_CUDA(c, cudaMemcpyAsync(&live, c->d_counters.p + (size_t)(b + 1) * CTR_STRIDE + CTR_EXT, 4,
+                                    cudaMemcpyDeviceToHost, c->stream));
+        HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (live == 0) break;
+      }
+    }
+    HJK_CUDA(c, cudaGetLastError());
+    if (do_recon) {
+      KernelTimer t(c, stats, HJK_K_RECON);
+      PassDev ps{};
+      ps.width = plan.width, ps.height = plan.height, ps.tile_w = plan.tile_w, ps.tile_h = plan.tile_h;
+      ps.tiles_x = plan.tiles_x, ps.tiles_y = plan.tiles_y;
+      ps.tile_block = w.tile_block;
+      ps.blocks = d_blocks;
+      ps.weights = c->d_weights.p;
+      ps.radius = R;
+      rc = launch_recon(c, ps, wp, w.layer0, w.layer1, nullptr, c->d_acc.p);
+      if (rc) return rc;
+      launches++;
+    }
+    // ray counts of this wave (the counters are reused by the next one)
+    if (stats) {
+      const size_t used = (size_t)(bounces_run + 1) * CTR_STRIDE;
+      HJK_CUDA(c, cudaMemcpyAsync(c->h_counters.data(), c->d_counters.p, used * 4, cudaMemcpyDeviceToHost,
+                                  c->stream));
+      HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+      n_paths += c->h_counters[CTR_EXT];
+      for (uint32_t b = 0; b < bounces_run; b++) {
+        n_ext += c->h_counters[(size_t)b * CTR_STRIDE + CTR_EXT];
+        n_sh += c->h_counters[(size_t)b * CTR_STRIDE + CTR_SHADOW];
+      }
+    }
+    c->last_wave_passes = wp;
+    c->have_features = true;
+  }
+  HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  if (!(prm->flags & HJK_RENDER_ASYNC) || stats) {
+    HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+    if (stats) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      stats->ms_total = ms;
+      stats->n_paths = n_paths;
+      stats->n_extension_rays = n_ext;
+      stats->n_shadow_rays = n_sh;
+      stats->n_launches = launches;
+    }
+  }
+  return HJK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hjk_version(void) { return "hijiki_b200 0.1 (sm_100a)"; }
+
+const char* hjk_last_error(const HjkContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
+  if (!out_ctx || n_devices != 1 || !device_ids) {
+    g_create_error = "hjk_create: exactly one device per context (one process per GPU)";
+    return HJK_ERR_INVALID_ARGUMENT;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return HJK_ERR_CUDA;
+  }
+  if (device_ids[0] < 0 || device_ids[0] >= count) {
+    g_create_error = "hjk_create: device id out of range";
+    return HJK_ERR_INVALID_ARGUMENT;
+  }
+  HjkContext* c = new (std::nothrow) HjkContext();
+  if (!c) return HJK_ERR_OUT_OF_MEMORY;
+  c->device = device_ids[0];
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete c;
+    return HJK_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  if (prop.major < 10) {
+    g_create_error = "hijiki_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+    delete c;
+    return HJK_ERR_UNSUPPORTED;
+  }
+  c->n_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  c->own_stream = true;
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  cudaEventCreate(&c->evk[0]);
+  cudaEventCreate(&c->evk[1]);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, kTravThreads, 0);
+  c->blocks_trav = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
+  c->blocks_tile = std::max(occ, 1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return bail("kernel image (built for sm_100a)", e);
+  *out_ctx = c;
+  return HJK_OK;
+}
+
+int hjk_destroy(HjkContext* c) {
+  if (!c) return HJK_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->resident)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->evk[0]);
+  cudaEventDestroy(c->evk[1]);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return HJK_OK;
+}
+
+int hjk_set_stream(HjkContext* c, void* cuda_stream) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)cuda_stream;
+  c->own_stream = false;
+  return HJK_OK;
+}
+
+int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!s || !s->scene.ptr || s->scene.count != 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "scene info missing");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  const HjkSceneInfo* info = (const HjkSceneInfo*)s->scene.ptr;
+  if (info->num_spheres != s->spheres.count || info->num_quads != s->quads.count ||
+      info->num_triangles != s->triangles.count || info->num_emitters != s->emitters.count)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "SceneBufferInfo counts disagree with the array counts");
+  const uint64_t n_shapes = s->spheres.count + s->quads.count + s->triangles.count;
+  if (s->materials.count != n_shapes)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "materials must hold one word per shape");
+  // validate material words and emitter table against the typed arrays they index
+  const uint32_t* mats = (const uint32_t*)s->materials.ptr;
+  bool has_ext = false;
+  for (uint64_t i = 0; i < n_shapes; i++) {
+    const uint32_t tag = mats[i] >> HJK_MATERIAL_TAG_SHIFT, idx = mats[i] & ((1u << HJK_MATERIAL_TAG_SHIFT) - 1u);
+    uint64_t limit = 1;
+    switch (tag) {
+      case HJK_MAT_DIFFUSE: limit = s->diffuse.count; break;
+      case HJK_MAT_DIFFUSECBOARD: limit = s->diffusecb.count; break;
+      case HJK_MAT_MIRROR: limit = 0xFFFFFFFFull; break;
+      case HJK_MAT_DIELECTRIC: limit = s->dielectric.count; break;
+      case HJK_MAT_EMISSIVE: limit = s->emissive.count; break;
+      default: return c->fail(HJK_ERR_INVALID_ARGUMENT, "shape %llu has unknown material tag %u", (unsigned long long)i, tag);
+    }
+    if (idx >= limit) return c->fail(HJK_ERR_INVALID_ARGUMENT, "shape %llu: material index out of range", (unsigned long long)i);
+  }
+  for (uint64_t i = 0; i < s->dielectric.count; i++) {
+    const HjkDielectric& d = ((const HjkDielectric*)s->dielectric.ptr)[i];
+    if (d.extinction_eta[0] != 0.f || d.extinction_eta[1] != 0.f || d.extinction_eta[2] != 0.f) has_ext = true;
+  }
+  for (uint64_t i = 0; i < s->emitters.count; i++) {
+    const HjkEmitter& e = ((const HjkEmitter*)s->emitters.ptr)[i];
+    if (e.shape >= n_shapes || (mats[e.shape] >> HJK_MATERIAL_TAG_SHIFT) != HJK_MAT_EMISSIVE)
+      return c->fail(HJK_ERR_INVALID_ARGUMENT, "emitter %llu does not point at an emissive shape", (unsigned long long)i);
+  }
+  WideBvh bvh;
+  std::string err;
+  if (!build_wide_bvh(*s, c->bvh_pad_rel, bvh, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+  if (bvh.depth > (uint32_t)kMaxStack)
+    return c->fail(HJK_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", bvh.depth, kMaxStack);
+
+  int rc;
+  HjkArray a_nodes{bvh.nodes.data(), bvh.nodes.size()}, a_prims{bvh.prims.data(), bvh.prims.size()};
+  if ((rc = upload(c, c->d_nodes, a_nodes, sizeof(WideNode)))) return rc;
+  if ((rc = upload(c, c->d_prims, a_prims, sizeof(WidePrim)))) return rc;
+  if ((rc = upload(c, c->d_spheres, s->spheres, 16))) return rc;
+  if ((rc = upload(c, c->d_quads, s->quads, 48))) return rc;
+  if ((rc = upload(c, c->d_triangles, s->triangles, 12))) return rc;
+  if ((rc = upload(c, c->d_vertices, s->vertices, 32))) return rc;
+  if ((rc = upload(c, c->d_materials, s->materials, 4))) return rc;
+  if ((rc = upload(c, c->d_emitters, s->emitters, 16))) return rc;
+  if ((rc = upload(c, c->d_diffuse, s->diffuse, 16))) return rc;
+  if ((rc = upload(c, c->d_diffusecb, s->diffusecb, 32))) return rc;
+  if ((rc = upload(c, c->d_dielectric, s->dielectric, 16))) return rc;
+  if ((rc = upload(c, c->d_emissive, s->emissive, 16))) return rc;
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+
+  SceneDev& d = c->scene;
+  d.nodes = c->d_nodes.p, d.prims = c->d_prims.p;
+  d.spheres = c->d_spheres.p, d.quads = c->d_quads.p, d.triangles = c->d_triangles.p;
+  d.vertices = c->d_vertices.p, d.materials = c->d_materials.p, d.emitters = c->d_emitters.p;
+  d.diffuse = c->d_diffuse.p, d.diffusecb = c->d_diffusecb.p, d.dielectric = c->d_dielectric.p;
+  d.emissive = c->d_emissive.p;
+  d.num_spheres = info->num_spheres, d.num_quads = info->num_quads;
+  d.num_triangles = info->num_triangles, d.num_emitters = info->num_emitters;
+  d.camera = info->camera;
+  c->has_extinction = has_ext;
+  c->n_nodes = bvh.nodes.size();
+  c->n_prims = bvh.prims.size();
+  bvh.nodes.clear();
+  bvh.nodes.shrink_to_fit();
+  bvh.prims.clear();
+  bvh.prims.shrink_to_fit();
+  c->bvh_host_stats = bvh;
+  c->has_scene = true;
+  return HJK_OK;
+}
+
+int hjk_frame_begin(HjkContext* c, uint32_t width, uint32_t height) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "unsupported frame size");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  c->have_features = false;
+  return ensure_frame(c, width, height, true);
+}
+
+int hjk_render(HjkContext* c, const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm, HjkStats* stats) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!blocks || n_blocks == 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "empty block list");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  HJK_CUDA(c, c->d_blocks.ensure(n_blocks));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_blocks.p, blocks, n_blocks * sizeof(HjkImageBlock), cudaMemcpyHostToDevice,
+                              c->stream));
+  return render_blocks(c, blocks, c->d_blocks.p, n_blocks, prm, stats);
+}
+
+int hjk_blocks_upload(HjkContext* c, const HjkImageBlock* blocks, uint64_t n_blocks, uint64_t* out_handle) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!blocks || n_blocks == 0 || !out_handle) return c->fail(HJK_ERR_INVALID_ARGUMENT, "empty block list");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  HjkContext::Resident r;
+  r.host.assign(blocks, blocks + n_blocks);
+  HJK_CUDA(c, cudaMalloc((void**)&r.dev, n_blocks * sizeof(HjkImageBlock)));
+  cudaError_t e = cudaMemcpy(r.dev, blocks, n_blocks * sizeof(HjkImageBlock), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(r.dev);
+    return c->fail(HJK_ERR_CUDA, "block upload failed: %s", cudaGetErrorString(e));
+  }
+  const uint64_t h = c->next_handle++;
+  c->resident[h] = std::move(r);
+  *out_handle = h;
+  return HJK_OK;
+}
+
+int hjk_render_resident(HjkContext* c, uint64_t handle, uint64_t first_block, uint64_t n_blocks,
+                        const HjkParams* prm, HjkStats* stats) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  auto it = c->resident.find(handle);
+  if (it == c->resident.end()) return c->fail(HJK_ERR_INVALID_ARGUMENT, "unknown block-list handle");
+  if (n_blocks == 0 || first_block + n_blocks > it->second.host.size())
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "block range out of bounds");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  return render_blocks(c, it->second.host.data() + first_block, it->second.dev + first_block, n_blocks, prm, stats);
+}
+
+int hjk_blocks_free(HjkContext* c, uint64_t handle) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  auto it = c->resident.find(handle);
+  if (it == c->resident.end()) return c->fail(HJK_ERR_INVALID_ARGUMENT, "unknown block-list handle");
+  cudaStreamSynchronize(c->stream);
+  cudaFree(it->second.dev);
+  c->resident.erase(it);
+  return HJK_OK;
+}
+
+int hjk_allreduce_accumulator(HjkContext* c, float* out_ms) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->d_acc.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
+  if (out_ms) *out_ms = 0.f;
+  if (!c->comm || c->n_ranks == 1) return HJK_OK;
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  const size_t n = (size_t)c->width * c->height * 4;
+  int r = g_nccl.AllReduce(c->d_acc.p, c->d_acc.p, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream);
+  if (r != 0) return c->fail(HJK_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+  if (out_ms) cudaEventElapsedTime(out_ms, c->ev0, c->ev1);
+  return HJK_OK;
+}
+
+int hjk_readback(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->d_acc.p) return c->fail(HJK_ERR_NO_FRAME, "hjk_readback before any frame");
+  if (!rgba || pitch_bytes < (uint64_t)c->width * 16) return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad destination");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  if (c->comm && c->n_ranks > 1) {
+    int rc = hjk_allreduce_accumulator(c, nullptr);
+    if (rc) return rc;
+  }
+  const uint32_t n = c->width * c->height;
+  const f4* src = c->d_acc.p;
+  if (normalise) {
+    HJK_CUDA(c, c->d_norm.ensure(n));
+    k_normalise<<<grid_for(c, 4), 256, 0, c->stream>>>(c->d_acc.p, c->d_norm.p, n);
+    HJK_CUDA(c, cudaGetLastError());
+    src = c->d_norm.p;
+  }
+  HJK_CUDA(c, cudaMemcpy2DAsync(rgba, pitch_bytes, src, (size_t)c->width * 16, (size_t)c->width * 16, c->height,
+                                cudaMemcpyDeviceToHost, c->stream));
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HJK_OK;
+}
+
+int hjk_read_intermediate(HjkContext* c, int layer, float* rgba) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->have_features || !c->last_wave_passes) return c->fail(HJK_ERR_NO_FRAME, "no pass has been rendered");
+  if (layer < 0 || layer > 2 || !rgba) return c->fail(HJK_ERR_INVALID_ARGUMENT, "layer must be 0, 1 or 2");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->width * c->height;
+  if (layer == 2) {  // albedo is never written by the integrator (render.glsl:84-85,174)
+    memset(rgba, 0, n * 16);
+    return HJK_OK;
+  }
+  const f4* src = (layer == 0 ? c->d_layer0.p : c->d_layer1.p) + (size_t)(c->last_wave_passes - 1) * n;
+  HJK_CUDA(c, cudaMemcpyAsync(rgba, src, n * 16, cudaMemcpyDeviceToHost, c->stream));
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HJK_OK;
+}
+
+int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int any_hit, int32_t* shape_id,
+                        float* t, float* uv) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->has_scene) return c->fail(HJK_ERR_NO_SCENE, "hjk_trace_first_hit before hjk_scene_upload");
+  if (!rays || !shape_id || n_rays == 0 || n_rays > 0x7FFFFFFFull)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad ray batch");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)n_rays;
+  std::vector<f4> ho(n), hd(n);
+  for (size_t i = 0; i < n; i++) {
+    ho[i] = F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min);
+    hd[i] = F4(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2], rays[i].t_max);
+  }
+  DevBuf<f4> d_o, d_d, d_h;
+  DevBuf<uint32_t> d_cur;
+  HJK_CUDA(c, d_o.ensure(n));
+  HJK_CUDA(c, d_d.ensure(n));
+  HJK_CUDA(c, d_h.ensure(n));
+  HJK_CUDA(c, d_cur.ensure(1));
+  HJK_CUDA(c, cudaMemcpyAsync(d_o.p, ho.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
+  HJK_CUDA(c, cudaMemcpyAsync(d_d.p, hd.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
+  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 4, c->stream));
+  const float eps = 1e-4f;  // M_EPS, math.glsl:2
+  if (any_hit)
+    k_trace_batch<true><<<grid_for(c, c->blocks_trav), kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p,
+                                                                                    (uint32_t)n, d_cur.p, eps);
+  else
+    k_trace_batch<false><<<grid_for(c, c->blocks_trav), kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p,
+                                                                                     (uint32_t)n, d_cur.p, eps);
+  HJK_CUDA(c, cudaGetLastError());
+  std::vector<f4> hh(n);
+  HJK_CUDA(c, cudaMemcpyAsync(hh.data(), d_h.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < n; i++) {
+    int32_t id;
+    memcpy(&id, &hh[i].x, 4);
+    if (any_hit) {
+      shape_id[i] = id >= 0 ? 1 : 0;
+    } else {
+      shape_id[i] = id;
+    }
+    if (t) t[i] = id >= 0 ? hh[i].y : 0.f;
+    if (uv) {
+      uv[2 * i] = id >= 0 ? hh[i].z : 0.f;
+      uv[2 * i + 1] = id >= 0 ? hh[i].w : 0.f;
+    }
+  }
+  return HJK_OK;
+}
+
+static int denoise_apply(HjkContext* c, const HjkParams* prm, uint32_t repeat, float* out_ms) {
+  PassPlan plan;
+  std::string err;
+  if (!plan_passes(c->dn_blocks.data(), c->dn_blocks.size(), plan, err))
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+  if (plan.passes.size() != 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "denoise blocks must form exactly one pass");
+  if (!(prm->recon_stddev > 0.f)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "recon_stddev must be positive");
+  int rc = ensure_frame(c, plan.width, plan.height, false);
+  if (rc) return rc;
+  const int R = (int)prm->recon_radius, taps = 2 * R + 1;
+  const size_t nb = c->dn_blocks.size();
+  HJK_CUDA(c, c->d_blocks.ensure(nb));
+  HJK_CUDA(c, c->d_weights.ensure(nb * taps * taps));
+  HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_blocks.p, c->dn_blocks.data(), nb * sizeof(HjkImageBlock), cudaMemcpyHostToDevice,
+                              c->stream));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_tile_block.p, plan.tile_block.data(), plan.tile_block.size() * 4,
+                              cudaMemcpyHostToDevice, c->stream));
+  k_recon_weights<<<std::max<int>(1, (int)std::min<size_t>(1024, (nb * taps * taps + 255) / 256)), 256, 0, c->stream>>>(
+      c->d_blocks.p, (uint32_t)nb, R, prm->recon_stddev, c->d_weights.p);
+  PassDev ps{};
+  ps.width = plan.width, ps.height = plan.height, ps.tile_w = plan.tile_w, ps.tile_h = plan.tile_h;
+  ps.tiles_x = plan.tiles_x, ps.tiles_y = plan.tiles_y;
+  ps.tile_block = c->d_tile_block.p;
+  ps.blocks = c->d_blocks.p;
+  ps.weights = c->d_weights.p;
+  ps.radius = R;
+  HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  for (uint32_t i = 0; i < repeat; i++) {
+    rc = launch_recon(c, ps, 1, c->d_dn0.p, c->d_dn1.p, c->dn_has_albedo ? c->d_dn2.p : nullptr, c->d_acc.p);
+    if (rc) return rc;
+  }
+  HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+  if (out_ms) cudaEventElapsedTime(out_ms, c->ev0, c->ev1);
+  return HJK_OK;
+}
+
+static int denoise_upload(HjkContext* c, const float* radiance, const float* normal_depth, const float* albedo,
+                          const HjkImageBlock* blocks, uint64_t n_blocks) {
+  if (!radiance || !normal_depth || !blocks || n_blocks == 0)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "denoise needs radiance, normal_depth and blocks");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)blocks[0].original_dimension[0] * blocks[0].original_dimension[1];
+  if (n == 0 || n > 0x7FFFFFFFull) return c->fail(HJK_ERR_INVALID_ARGUMENT, "unsupported image size");
+  HJK_CUDA(c, c->d_dn0.ensure(n));
+  HJK_CUDA(c, c->d_dn1.ensure(n));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_dn0.p, radiance, n * 16, cudaMemcpyHostToDevice, c->stream));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_dn1.p, normal_depth, n * 16, cudaMemcpyHostToDevice, c->stream));
+  c->dn_has_albedo = albedo != nullptr;
+  if (albedo) {
+    HJK_CUDA(c, c->d_dn2.ensure(n));
+    HJK_CUDA(c, cudaMemcpyAsync(c->d_dn2.p, albedo, n * 16, cudaMemcpyHostToDevice, c->stream));
+  }
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->dn_blocks.assign(blocks, blocks + n_blocks);
+  return HJK_OK;
+}
+
+int hjk_denoise_pass(HjkContext* c, const float* radiance, const float* normal_depth, const float* albedo,
+                     const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!prm) return c->fail(HJK_ERR_INVALID_ARGUMENT, "params is null");
+  int rc = denoise_upload(c, radiance, normal_depth, albedo, blocks, n_blocks);
+  if (rc) return rc;
+  return denoise_apply(c, prm, 1, nullptr);
+}
+
+int hjk_denoise_upload(HjkContext* c, const float* radiance, const float* normal_depth, const HjkImageBlock* blocks,
+                       uint64_t n_blocks) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  return denoise_upload(c, radiance, normal_depth, nullptr, blocks, n_blocks);
+}
+
+int hjk_denoise_resident(HjkContext* c, const HjkParams* prm, uint32_t repeat, float* out_ms) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!prm || repeat == 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (c->dn_blocks.empty()) return c->fail(HJK_ERR_NO_FRAME, "hjk_denoise_resident before hjk_denoise_upload");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  return denoise_apply(c, prm, repeat, out_ms);
+}
+
+int hjk_comm_unique_id(void* out_id128) {
+  std::string err;
+  if (!out_id128 || !load_nccl(err)) {
+    g_create_error = err.empty() ? "null id buffer" : err;
+    return HJK_ERR_NCCL;
+  }
+  int r = g_nccl.GetUniqueId(out_id128);
+  if (r != 0) {
+    g_create_error = "ncclGetUniqueId failed";
+    return HJK_ERR_NCCL;
+  }
+  return HJK_OK;
+}
+
+int hjk_comm_init(HjkContext* c, const void* id128, int rank, int n_ranks) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad rank/size");
+  std::string err;
+  if (!load_nccl(err)) return c->fail(HJK_ERR_NCCL, "%s", err.c_str());
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  Id128 id;
+  memcpy(id.bytes, id128, 128);
+  int r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+  if (r != 0) return c->fail(HJK_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  c->rank = rank;
+  c->n_ranks = n_ranks;
+  return HJK_OK;
+}
+
+int hjk_accumulator_device_ptr(HjkContext* c, uint64_t* out_ptr, uint64_t* out_n_floats) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->d_acc.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
+  if (out_ptr) *out_ptr = (uint64_t)(uintptr_t)c->d_acc.p;
+  if (out_n_floats) *out_n_floats = (uint64_t)c->width * c->height * 4;
+  return HJK_OK;
+}
+
+int hjk_synchronize(HjkContext* c) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HJK_OK;
+}
+
+int hjk_set_profiling(HjkContext* c, int enabled) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  c->profiling = enabled != 0;
+  return HJK_OK;
+}
+
+int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
+  if (!c || !key) return HJK_ERR_INVALID_ARGUMENT;
+  const std::string k(key);
+  if (k == "wave_paths") {
+    if (value < 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "wave_paths must be positive");
+    c->wave_paths = (uint64_t)value;
+  } else if (k == "bvh_pad_rel_e9") {  // relative primitive-box pad in units of 1e-9 (next scene upload)
+    if (value < 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "pad must be non-negative");
+    c->bvh_pad_rel = (float)value * 1e-9f;
+  } else if (k == "blocks_per_sm_traverse") {
+    if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->blocks_trav = (int)value;
+  } else if (k == "blocks_per_sm_tile") {
+    if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->blocks_tile = (int)value;
+  } else {
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "unknown option '%s'", key);
+  }
+  return HJK_OK;
+}
+
+int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
+  if (!c || !key || !out) return HJK_ERR_INVALID_ARGUMENT;
+  const std::string k(key);
+  if (k == "n_sms") *out = c->n_sms;
+  else if (k == "bvh_nodes") *out = (int64_t)c->n_nodes;
+  else if (k == "bvh_prims") *out = (int64_t)c->n_prims;
+  else if (k == "bvh_depth") *out = c->bvh_host_stats.depth;
+  else if (k == "bvh_bytes") *out = (int64_t)(c->n_nodes * sizeof(WideNode) + c->n_prims * sizeof(WidePrim));
+  else if (k == "blocks_per_sm_traverse") *out = c->blocks_trav;
+  else if (k == "blocks_per_sm_tile") *out = c->blocks_tile;
+  else if (k == "wave_paths") *out = (int64_t)c->wave_paths;
+  else if (k == "has_extinction") *out = c->has_extinction ? 1 : 0;
+  else if (k == "device") *out = c->device;
+  else if (k == "width") *out = c->width;
+  else if (k == "height") *out = c->height;
+  else return c->fail(HJK_ERR_INVALID_ARGUMENT, "unknown info key '%s'", key);
+  return HJK_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "host_scene.h"
+#include "wide_bvh_host.h"
 
 struct HjkHostScene {
   hjk::CompiledScene compiled;
@@ -103,6 +104,33 @@ int hjk_host_scene_view(const HjkHostScene* hs, HjkScene* v) {
   v->dielectric = view_of(c.dielectric);
   v->emissive = view_of(c.emissive);
   return HJK_OK;
+}
+
+int hjk_host_bvh_stats(const HjkScene* scene, float pad_rel, uint64_t* out6) {
+  if (!scene || !out6) {
+    g_host_error = "hjk_host_bvh_stats: null argument";
+    return HJK_ERR_INVALID_ARGUMENT;
+  }
+  try {
+    hjk::WideBvh bvh;
+    std::string err;
+    if (!hjk::build_wide_bvh(*scene, pad_rel < 0.f ? hjk::kDefaultBvhPadRel : pad_rel, bvh, err)) {
+      g_host_error = err;
+      return HJK_ERR_INVALID_ARGUMENT;
+    }
+    const bool ok = hjk::validate_wide_bvh(*scene, bvh, err);
+    if (!ok) g_host_error = err;
+    out6[0] = bvh.nodes.size();
+    out6[1] = bvh.prims.size();
+    out6[2] = bvh.depth;
+    out6[3] = ok ? 1 : 0;
+    out6[4] = (uint64_t)(bvh.sah_cost * 1000.f);
+    out6[5] = bvh.nodes.size() * sizeof(hjk::WideNode) + bvh.prims.size() * sizeof(hjk::WidePrim);
+    return HJK_OK;
+  } catch (const std::exception& e) {
+    g_host_error = e.what();
+    return HJK_ERR_OUT_OF_MEMORY;
+  }
 }
 
 int hjk_host_scene_free(HjkHostScene* hs) {

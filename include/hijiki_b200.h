@@ -196,7 +196,8 @@ enum {
   HJK_K_SHADE = 2,
   HJK_K_SHADOW = 3,
   HJK_K_RECON = 4,
-  HJK_K_OTHER = 5
+  HJK_K_OTHER = 5,
+  HJK_K_SORT = 6 /* material binning / queue compaction */
 };
 
 typedef struct HjkStats {
@@ -290,6 +291,9 @@ HJK_API int hjk_allreduce_accumulator(HjkContext* ctx, float* out_ms);
  * owns a communicator (e.g. torch.distributed) can reduce it in place. */
 HJK_API int hjk_accumulator_device_ptr(HjkContext* ctx, uint64_t* out_ptr, uint64_t* out_n_floats);
 HJK_API int hjk_synchronize(HjkContext* ctx);
+/* Run on a stream the host owns (a cudaStream_t, e.g. torch.cuda.Stream.cuda_stream) instead
+ * of the context's private stream, so the host's own events and collectives order with it. */
+HJK_API int hjk_set_stream(HjkContext* ctx, void* cuda_stream);
 
 /* ----------------------------------------------------- misc / profiling */
 HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-event timing */
@@ -317,6 +321,12 @@ HJK_API int hjk_host_scene_spheres(uint32_t lattice_n, uint64_t seed, int with_b
 HJK_API int hjk_host_scene_view(const HjkHostScene* scene, HjkScene* out_view);
 HJK_API int hjk_host_scene_free(HjkHostScene* scene);
 HJK_API const char* hjk_host_last_error(void);
+
+/* Builds the 8-wide compressed BVH on the host (what hjk_scene_upload does) and reports
+ * out[0] nodes, out[1] primitive records, out[2] depth, out[3] 1 if the structural check
+ * passed (every shape reachable once, every box contains what is below it),
+ * out[4] root SAH cost x 1000, out[5] bytes.  pad_rel < 0 selects the default pad. */
+HJK_API int hjk_host_bvh_stats(const HjkScene* scene, float pad_rel, uint64_t* out6);
 
 /* ImageBlockGenerator (src/main.rs:619-682) with the OS-entropy draws replaced
  * by a recorded splitmix64 stream from `root_seed`.  Returns the block count

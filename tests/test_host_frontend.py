@@ -1,0 +1,119 @@
+"""Host logic (no GPU): block generator, pass planning, EXR writer, sample-pass split, and that the
+C-ABI library loads and exports every symbol include/hijiki_b200.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import _libs
+import hijiki_b200 as hj
+from hijiki_b200 import _abi
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _abi.load()  # raises if the in-tree .so is missing
+    header = open(os.path.join(_libs.ROOT, "include", "hijiki_b200.h")).read()
+    declared = set(re.findall(r"HJK_API\s+[\w\s\*]+?\b(hjk_\w+)\s*\(", header))
+    assert declared, "no HJK_API declarations found"
+    assert declared == set(_abi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.hjk_version()
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    """Without a CUDA device the product refuses to run — there is no CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hj.HijikiError):
+        hj.Context(0)
+
+
+def test_block_generator_matches_reference_iteration():
+    """ImageBlockGenerator::next (src/main.rs:648-682): row-major tiles, spp passes, clipped edges,
+    one sample_offset per pass — re-drawn BEFORE the last block of the pass is emitted."""
+    gen = hj.ImageBlockGenerator(1920, 1080, 128, 3)
+    b = gen.blocks()
+    assert gen.blocks_per_pass == 135 and b.size == 405
+    assert (b["id"] == np.arange(405)).all()
+    first = b[:135]
+    assert (first["origin"][:, 0] == np.tile(np.arange(15) * 128, 9)).all()
+    assert (first["origin"][:, 1] == np.repeat(np.arange(9) * 128, 15)).all()
+    assert (first["dimension"][:, 0] == 128).all()
+    assert (first["dimension"][-15:, 1] == 56).all() and (first["dimension"][:-15, 1] == 128).all()
+    assert (b["original_dimension"] == (1920, 1080)).all()
+    so = b["sample_offset"]
+    assert (so >= 0).all() and (so < 1).all()
+    assert (so[:134] == so[0]).all()
+    assert (so[134] == so[135]).all() and not (so[134] == so[0]).all()  # the quirk
+    assert len(set(b["seed"].tolist())) > 400
+    # recorded stream: same root seed, same list
+    assert (hj.ImageBlockGenerator(1920, 1080, 128, 3).blocks() == b).all()
+    assert not (hj.ImageBlockGenerator(1920, 1080, 128, 3, root_seed=1).blocks()["seed"] == b["seed"]).all()
+    with pytest.raises(ValueError):
+        hj.ImageBlockGenerator(100, 100, 100, 1)
+
+
+def test_split_passes_partitions_every_pass_once():
+    gen = hj.ImageBlockGenerator(300, 200, 64, 7)
+    b = gen.blocks()
+    parts = [hj.split_passes(b, gen.blocks_per_pass, r, 4) for r in range(4)]
+    ids = np.concatenate([p["id"] for p in parts])
+    assert sorted(ids.tolist()) == list(range(b.size))
+    assert [p.size // gen.blocks_per_pass for p in parts] == [2, 2, 2, 1]
+    assert (hj.split_passes(b, gen.blocks_per_pass, 0, 1) == b).all()
+
+
+def test_exr_writer_roundtrip(tmp_path):
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    cv2 = pytest.importorskip("cv2")
+    lib = _abi.load()
+    rng = np.random.default_rng(3)
+    img = rng.random((37, 53, 4), dtype=np.float32)
+    path = str(tmp_path / "out.exr")
+    assert lib.hjk_host_write_exr(path.encode(), _abi.as_ptr(img), 53, 37, img.strides[0]) == 0
+    back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if back is None:
+        pytest.skip("this cv2 build cannot read EXR")
+    assert back.shape == (37, 53, 3)
+    assert np.array_equal(back[..., ::-1], img[..., :3])  # cv2 returns BGR
+    assert lib.hjk_host_write_exr(b"/nonexistent_dir/x.exr", _abi.as_ptr(img), 53, 37, img.strides[0]) == -7
+
+
+def test_scene_errors_are_reported_not_thrown():
+    lib = _abi.load()
+    h = C.c_void_p()
+    assert lib.hjk_host_scene_from_obj(b"/no/such/file.obj", 0, 0, C.byref(h)) != 0
+    assert lib.hjk_host_last_error()
+    assert lib.hjk_host_scene_terrain(0, 1, 0, C.byref(h)) == -1
+    with pytest.raises(hj.HijikiError):
+        hj.Scene.from_obj("/no/such/file.obj").compile()
+
+
+@pytest.mark.parametrize("kind", ["cbox", "cbox_spheres", "spheres", "terrain"])
+def test_wide_bvh_is_structurally_valid(kind):
+    scene = {"cbox": hj.Scene.from_obj(_libs.CBOX_OBJ), "cbox_spheres": hj.Scene.from_obj(_libs.CBOX_OBJ, True),
+             "spheres": hj.Scene.spheres(8), "terrain": hj.Scene.terrain(96)}[kind].compile()
+    st = scene.bvh_stats()
+    info = scene.info
+    n = info.num_spheres + info.num_quads + info.num_triangles
+    assert st["valid"], _abi.load().hjk_host_last_error()
+    assert st["prims"] == n
+    assert st["depth"] <= 32 and st["nodes"] < n
+    assert st["bytes"] == st["nodes"] * 80 + st["prims"] * 48
+
+
+def test_synthetic_scene_shapes():
+    sp = hj.Scene.spheres(8).compile()
+    assert sp.info.num_spheres == 512 and sp.info.num_triangles == 4 and sp.info.num_emitters == 2
+    tags = sp.array("materials")[:512, 0] >> 24
+    assert set(tags.tolist()) == {_abi.MAT_MIRROR, _abi.MAT_DIELECTRIC}
+    assert np.allclose(sp.array("dielectric")[0], (0, 0, 0, 1.5))
+    r = sp.array("spheres")[:, 3]
+    assert r.min() >= 0.25 and r.max() <= 0.42
+    te = hj.Scene.terrain(64).compile()
+    assert te.info.num_triangles == 2 * 64 * 64 + 32 and te.info.num_emitters == 32
+    assert te.array("vertices").shape[0] == 65 * 65 + 16 * 4
