@@ -87,7 +87,10 @@ struct HjkContext {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk[2] = {nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;  // per-stage timing (profiling on)
+  std::vector<int> ev_slot;
+  size_t ev_used = 0;
   int n_sms = 0;
   int blocks_trav = 0, blocks_tile = 0;  // resident CTAs per SM of the persistent kernels
   std::string error;
@@ -171,23 +174,39 @@ int upload(HjkContext* c, DevBuf<T>& buf, const HjkArray& a, size_t elem_bytes) 
 
 int grid_for(const HjkContext* c, int per_sm) { return c->n_sms * std::max(per_sm, 1); }
 
-struct KernelTimer {  // per-stage CUDA-event timing, only when profiling is on
+// Per-stage device timing without host synchronisation: when profiling is on, every stage is
+// bracketed by a pair of events taken from a pool; the pairs are resolved after the call's
+// final synchronise.  Costs two event records per launch, no bubbles.
+struct KernelTimer {
   HjkContext* c;
-  HjkStats* st;
-  int slot;
-  KernelTimer(HjkContext* c_, HjkStats* st_, int slot_) : c(c_), st(st_), slot(slot_) {
-    if (c->profiling && st) cudaEventRecord(c->evk[0], c->stream);
+  bool on;
+  KernelTimer(HjkContext* c_, HjkStats* st, int slot) : c(c_), on(c_->profiling && st != nullptr) {
+    if (!on) return;
+    if (c->ev_used + 2 > c->ev_pool.size()) {
+      const size_t grow = c->ev_pool.size() + 256;
+      while (c->ev_pool.size() < grow) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+      }
+    }
+    c->ev_slot.push_back(slot);
+    cudaEventRecord(c->ev_pool[c->ev_used++], c->stream);
   }
   ~KernelTimer() {
-    if (c->profiling && st) {
-      cudaEventRecord(c->evk[1], c->stream);
-      cudaEventSynchronize(c->evk[1]);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
-      st->kernel_ms[slot] += ms;
-    }
+    if (on) cudaEventRecord(c->ev_pool[c->ev_used++], c->stream);
   }
 };
+void resolve_timers(HjkContext* c, HjkStats* st) {  // after the stream has been synchronised
+  if (st)
+    for (size_t i = 0; i < c->ev_slot.size(); i++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]) == cudaSuccess)
+        st->kernel_ms[c->ev_slot[i]] += ms;
+    }
+  c->ev_slot.clear();
+  c->ev_used = 0;
+}
 
 int ensure_frame(HjkContext* c, uint32_t w, uint32_t h, bool zero) {
   const size_t n = (size_t)w * h;
@@ -366,6 +385,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       HJK_CUDA(c, cudaMemcpyAsync(c->h_counters.data(), c->d_counters.p, used * 4, cudaMemcpyDeviceToHost,
                                   c->stream));
       HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+      resolve_timers(c, stats);
       n_paths += c->h_counters[CTR_EXT];
       for (uint32_t b = 0; b < bounces_run; b++) {
         n_ext += c->h_counters[(size_t)b * CTR_STRIDE + CTR_EXT];
@@ -378,6 +398,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   if (!(prm->flags & HJK_RENDER_ASYNC) || stats) {
     HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+    resolve_timers(c, stats);
     if (stats) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -435,8 +456,6 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   c->own_stream = true;
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
-  cudaEventCreate(&c->evk[0]);
-  cudaEventCreate(&c->evk[1]);
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, kTravThreads, 0);
   c->blocks_trav = std::max(occ, 1);
@@ -456,8 +475,7 @@ int hjk_destroy(HjkContext* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
-  cudaEventDestroy(c->evk[0]);
-  cudaEventDestroy(c->evk[1]);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return HJK_OK;

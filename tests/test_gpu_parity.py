@@ -1,0 +1,270 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs (bit-exact; ties excluded and counted), plus size-independent properties at
+BASELINE.json's full sizes.  Needs a B200; nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _libs
+import hijiki_b200 as hj
+from hijiki_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _compiled(kind):
+    if kind == "cbox":
+        return hj.Scene.from_obj(_libs.CBOX_OBJ).compile(use_bvh=True)
+    if kind == "cbox_spheres":
+        return hj.Scene.from_obj(_libs.CBOX_OBJ, put_cbox_spheres=True).compile(use_bvh=True)
+    if kind == "spheres":
+        return hj.Scene.spheres(4).compile(use_bvh=True)
+    if kind == "terrain":
+        return hj.Scene.terrain(64).compile(use_bvh=True)
+    raise KeyError(kind)
+
+
+def _random_rays(compiled, n, seed):
+    rng = np.random.default_rng(seed)
+    v = compiled.array("vertices")[:, :3]
+    lo, hi = v.min(axis=0) - 0.5, v.max(axis=0) + 0.5
+    rays = np.zeros(n, dtype=_abi.RAY_DTYPE)
+    rays["origin"] = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    d = rng.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["direction"] = d.astype(np.float32)
+    rays["t_min"] = 2e-4
+    rays["t_max"] = np.inf
+    rays["direction"][:6] = np.eye(3, dtype=np.float32).repeat(2, axis=0) * np.array([1, -1] * 3)[:, None]
+    return rays
+
+
+def _oracle_trace(compiled, rays, mode):
+    O = _libs.oracle()
+    n = rays.size
+    ids, t, uv, tie = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
+    assert O.orc_trace(C.byref(compiled.view), _libs.ptr(rays), n, mode, 1e-4, _libs.ptr(ids), _libs.ptr(t),
+                       _libs.ptr(uv), _libs.ptr(tie), 0) == 0
+    return ids, t, uv, tie
+
+
+@pytest.mark.parametrize("kind,mode", [("cbox", 0), ("cbox_spheres", 0), ("spheres", 2), ("terrain", 2)])
+def test_first_hit_ids_bit_exact(gpu_ctx, kind, mode):
+    """North star: first-hit primitive ids on a fixed ray batch bit-exact vs the reference arithmetic
+    (linear scan = the reference default, scene.glsl:134-157); ties excluded and counted."""
+    compiled = _compiled(kind)
+    gpu_ctx.scene_upload(compiled)
+    scene = _libs.HostScene.__new__(_libs.HostScene)
+    scene.view, scene.handle, scene.lib = compiled.view, None, None
+    rays = np.concatenate([_libs.camera_rays(scene, 160, 90), _random_rays(compiled, 20000, 5)])
+    ids_o, t_o, uv_o, tie = _oracle_trace(compiled, rays, mode)
+    ids_g, t_g, uv_g = gpu_ctx.trace_first_hit(rays)
+    keep = tie == 0
+    print(f"{kind}: {rays.size} rays, {int(tie.sum())} ties excluded, "
+          f"{int((ids_o[~keep] != ids_g[~keep]).sum())} of them resolved differently")
+    assert tie.sum() < 0.002 * rays.size
+    assert (ids_o[keep] == ids_g[keep]).all()
+    hit = keep & (ids_o >= 0)
+    assert hit.sum() > 0.3 * rays.size
+    assert (t_o[hit].view(np.uint32) == t_g[hit].view(np.uint32)).all()
+    tri = hit & (ids_o >= compiled.info.num_spheres)
+    assert (uv_o[tri].view(np.uint32) == uv_g[tri].view(np.uint32)).all()
+
+
+def test_shadow_rays_exact(gpu_ctx):
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    rays = _random_rays(compiled, 50000, 9)
+    rays["t_max"] = (np.random.default_rng(1).random(rays.size) * 3).astype(np.float32)
+    occ = np.zeros(rays.size, np.uint8)
+    O = _libs.oracle()
+    assert O.orc_occluded(C.byref(compiled.view), _libs.ptr(rays), rays.size, 0, 1e-4, _libs.ptr(occ), 0) == 0
+    ids_g, _, _ = gpu_ctx.trace_first_hit(rays, any_hit=True)
+    assert (ids_g == occ).all()
+
+
+def _oracle_render(compiled, blocks, max_bounces, bs, use_bvh):
+    O = _libs.oracle()
+    w, h = int(blocks[0]["original_dimension"][0]), int(blocks[0]["original_dimension"][1])
+    acc = np.zeros((h, w, 4), np.float32)
+    st = _libs.OrcStats()
+    op = _libs.orc_params(max_bounces=max_bounces, use_bvh=use_bvh, block_size=bs)
+    assert O.orc_render(C.byref(compiled.view), _libs.ptr(blocks), blocks.size, C.byref(op), _libs.ptr(acc),
+                        C.byref(st), 0) == 0
+    return acc, st
+
+
+@pytest.mark.parametrize("kind,max_bounces,use_bvh,wave_paths", [
+    ("cbox", 8, 0, 4 << 20), ("cbox", 1000, 0, 4 << 20), ("cbox_spheres", 1000, 0, 10000), ("spheres", 16, 2, 4 << 20),
+])
+def test_render_accumulator_matches_oracle(gpu_ctx, kind, max_bounces, use_bvh, wave_paths):
+    """hjk_render vs the oracle's Renderer::render on the same block list: equal ray counts and a
+    bit-identical accumulator, tie-affected samples excepted (each touches <= 25 texels)."""
+    compiled = _compiled(kind)
+    gpu_ctx.scene_upload(compiled)
+    gpu_ctx.set_option("wave_paths", wave_paths)  # 10000 forces one pass per wave, several waves
+    w, h, bs, spp = 136, 100, 64, 3
+    blocks = hj.ImageBlockGenerator(w, h, bs, spp).blocks()
+    gpu_ctx.frame_begin(w, h)
+    st = gpu_ctx.render(blocks, hj.make_params(max_bounces=max_bounces))
+    acc_g = gpu_ctx.readback(normalise=False)
+    acc_o, ost = _oracle_render(compiled, blocks, max_bounces, bs, use_bvh)
+    gpu_ctx.set_option("wave_paths", 4 << 20)
+    diff = (acc_o.view(np.uint32) != acc_g.view(np.uint32)).any(axis=2)
+    print(f"{kind}/{max_bounces}: texels differing {int(diff.sum())}/{diff.size}; rays gpu "
+          f"{st.n_extension_rays}+{st.n_shadow_rays} oracle {ost.n_extension_rays}+{ost.n_shadow_rays}")
+    assert st.n_paths == ost.n_paths == w * h * spp
+    assert diff.sum() <= 25 * 4
+    if diff.sum() == 0:
+        assert st.n_extension_rays == ost.n_extension_rays and st.n_shadow_rays == ost.n_shadow_rays
+    assert abs(st.n_extension_rays - ost.n_extension_rays) <= 100
+    img = gpu_ctx.readback(normalise=True)
+    ref = acc_o[..., :3] / acc_o[..., 3:4]
+    same = ~diff
+    assert np.array_equal(img[..., :3][same], ref[same])  # save_image's divide, src/main.rs:1399
+
+
+def test_intermediate_layers_match_oracle(gpu_ctx):
+    """render.glsl:172-174 outputs of one pass: radiance/1, normal/depth, albedo == 0."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h, bs = 128, 96, 64
+    blocks = hj.ImageBlockGenerator(w, h, bs, 1).blocks()
+    gpu_ctx.frame_begin(w, h)
+    gpu_ctx.render(blocks, hj.make_params(max_bounces=6, flags=hj.HJK_RENDER_NO_RECON))
+    O = _libs.oracle()
+    layers = np.zeros((3, h, w, 4), np.float32)
+    op = _libs.orc_params(max_bounces=6, use_bvh=0, block_size=bs)
+    assert O.orc_integrate_frame(C.byref(compiled.view), _libs.ptr(blocks), blocks.size, C.byref(op),
+                                 _libs.ptr(layers), None, 0) == 0
+    for layer in range(3):
+        got = gpu_ctx.read_intermediate(layer)
+        bad = (got.view(np.uint32) != layers[layer].view(np.uint32)).any(axis=2).sum()
+        assert bad <= 2, (layer, bad)
+    assert not gpu_ctx.readback(normalise=False).any()  # NO_RECON leaves the accumulator untouched
+
+
+def test_denoise_pass_matches_oracle(gpu_ctx):
+    w, h, bs = 150, 70, 64
+    rng = np.random.default_rng(11)
+    blocks = hj.ImageBlockGenerator(w, h, bs, 2).blocks()[:6]
+    rad = np.exp(rng.standard_normal((h, w, 4))).astype(np.float32)
+    rad[..., 3] = 1.0
+    rad[10, 20, 0] = np.nan
+    nrm = rng.standard_normal((h, w, 4)).astype(np.float32)
+    nrm[..., :3] /= np.linalg.norm(nrm[..., :3], axis=2, keepdims=True)
+    alb = rng.random((h, w, 4)).astype(np.float32)
+    O = _libs.oracle()
+    for albedo in (None, alb):
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.denoise_pass(rad, nrm, albedo, blocks, hj.make_params())
+        gpu_ctx.denoise_pass(rad, nrm, albedo, blocks, hj.make_params())  # ADDS (read-modify-write)
+        acc_o = np.zeros((h, w, 4), np.float32)
+        op = _libs.orc_params(block_size=bs)
+        for _ in range(2):
+            assert O.orc_reconstruct_frame(_libs.ptr(blocks), blocks.size, C.byref(op), _libs.ptr(rad), _libs.ptr(nrm),
+                                           _libs.ptr(albedo) if albedo is not None else None, _libs.ptr(acc_o), 0) == 0
+        assert np.array_equal(acc_o.view(np.uint32), gpu_ctx.readback(normalise=False).view(np.uint32))
+
+
+def test_device_math_matches_spec_bitwise(gpu_ctx):
+    """The device build of hjk_math.cuh == oracle/orc_math.h, through the only place it surfaces
+    directly: the reconstruction weights (exp) — checked via a one-texel splat."""
+    O = _libs.oracle()
+    w = h = 64
+    for so in [(0.0, 0.0), (0.5, 0.5), (0.123, 0.877), (0.999, 0.001)]:
+        blocks = hj.ImageBlockGenerator(w, h, 64, 1).blocks()
+        blocks["sample_offset"] = so
+        rad = np.zeros((h, w, 4), np.float32)
+        rad[32, 32] = (1, 1, 1, 1)
+        nrm = np.zeros((h, w, 4), np.float32)
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.denoise_pass(rad, nrm, None, blocks, hj.make_params())
+        acc = gpu_ctx.readback(normalise=False)
+        wts = np.zeros(25, np.float32)
+        O.orc_recon_spatial_weights(2, 0.5, so[0], so[1], _libs.ptr(wts))
+        # output texel (32-dx, 32-dy) receives tap (dx, dy)
+        for dx in range(-2, 3):
+            for dy in range(-2, 3):
+                wt = wts[(dx + 2) * 5 + (dy + 2)]
+                expect = np.float32(0.0) if wt < 0 else wt
+                assert acc[32 - dy, 32 - dx, 3].view(np.uint32) == np.float32(expect).view(np.uint32)
+
+
+def test_render_is_deterministic_and_wave_invariant(gpu_ctx):
+    """Same block list -> same bits, whatever the wave size (queue order differs, results do not)."""
+    compiled = _compiled("cbox_spheres")
+    gpu_ctx.scene_upload(compiled)
+    w, h = 200, 120
+    blocks = hj.ImageBlockGenerator(w, h, 64, 4).blocks()
+    outs = []
+    for wave in (4 << 20, 30000, 4 << 20):
+        gpu_ctx.set_option("wave_paths", wave)
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.render(blocks, hj.make_params(max_bounces=12))
+        outs.append(gpu_ctx.readback(normalise=False))
+    gpu_ctx.set_option("wave_paths", 4 << 20)
+    assert np.array_equal(outs[0], outs[2])
+    # different wave sizes change how many passes one reconstruction launch folds, not the add order
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_sample_pass_split_is_linear(gpu_ctx):
+    """rendering passes p = r mod N on N contexts and summing the accumulators equals the
+    single-context frame up to fp32 summation order."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h = 160, 96
+    gen = hj.ImageBlockGenerator(w, h, 64, 4)
+    blocks = gen.blocks()
+    gpu_ctx.frame_begin(w, h)
+    gpu_ctx.render(blocks, hj.make_params(max_bounces=8))
+    full = gpu_ctx.readback(normalise=False)
+    total = np.zeros_like(full, dtype=np.float64)
+    for r in range(2):
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.render(hj.split_passes(blocks, gen.blocks_per_pass, r, 2), hj.make_params(max_bounces=8))
+        total += gpu_ctx.readback(normalise=False)
+    assert np.allclose(total, full, rtol=2e-6, atol=1e-6)
+
+
+def test_full_size_pass_properties(gpu_ctx):
+    """BASELINE config 2 geometry (cbox 1920x1080, max 8 bounces), two passes: every texel gets weight,
+    radiance is finite and non-negative, per-texel weight stays below the analytic tap-sum bound."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h = 1920, 1080
+    blocks = hj.ImageBlockGenerator(w, h, 128, 2).blocks()
+    gpu_ctx.frame_begin(w, h)
+    st = gpu_ctx.render(blocks, hj.make_params(max_bounces=8))
+    acc = gpu_ctx.readback(normalise=False)
+    assert st.n_paths == 2 * w * h
+    assert 2 * w * h <= st.n_extension_rays <= 8 * 2 * w * h
+    assert 0 < st.n_shadow_rays <= st.n_extension_rays
+    assert np.isfinite(acc).all() and (acc >= 0).all()
+    assert (acc[..., 3] > 0).all()
+    assert acc[..., 3].max() <= 2 * 1.7
+    img = acc[..., :3] / acc[..., 3:4]
+    assert 0.05 < img.mean() < 1.0
+    print(f"1080p x2 passes: {st.n_rays / 1e6:.1f} Mrays in {st.ms_total:.2f} ms = {st.mrays_per_s:.0f} Mrays/s")
+
+
+def test_error_paths_return_codes(gpu_ctx):
+    lib = gpu_ctx.lib
+    fresh = hj.Context(0)
+    with pytest.raises(hj.HijikiError) as e:
+        fresh.render(hj.ImageBlockGenerator(64, 64, 64, 1).blocks(), hj.make_params())
+    assert e.value.status == -3  # HJK_ERR_NO_SCENE
+    with pytest.raises(hj.HijikiError) as e:
+        fresh.readback()
+    assert e.value.status == -4
+    fresh.close()
+    bad = hj.ImageBlockGenerator(64, 64, 64, 1).blocks()
+    bad["origin"][0] = (32, 0)  # sticks out of the image
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    with pytest.raises(hj.HijikiError) as e:
+        gpu_ctx.render(bad, hj.make_params())
+    assert e.value.status == -1
+    assert lib.hjk_destroy(None) == 0
