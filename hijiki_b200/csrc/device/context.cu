@@ -557,6 +557,8 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   d.num_spheres = info->num_spheres, d.num_quads = info->num_quads;
   d.num_triangles = info->num_triangles, d.num_emitters = info->num_emitters;
   d.camera = info->camera;
+  for (int k = 0; k < 4; k++) d.sph_centre[k] = bvh.sph_centre[k];
+  d.sph_rmin = bvh.sph_rmin, d.sph_rmax = bvh.sph_rmax;
   c->has_extinction = has_ext;
   c->n_nodes = bvh.nodes.size();
   c->n_prims = bvh.prims.size();

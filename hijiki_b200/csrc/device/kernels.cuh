@@ -171,7 +171,7 @@ struct ExtendIO {  // closest hit over the extension queue of `bounce`
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
     const uint32_t slot = queue[i] & 0x7FFFFFFFu;
     s.slot = slot;
-    trav_init(s, w.ray_o[slot], w.ray_d[slot]);
+    trav_init(s, w.scene, w.ray_o[slot], w.ray_d[slot]);
   }
   __device__ __forceinline__ void store(const TravState& s) const {
     w.hit[s.slot] = F4(__int_as_float(s.hit_id), s.hit_t, s.hit_u, s.hit_v);
@@ -181,7 +181,7 @@ struct ShadowIO {  // any hit over the dense shadow queue; visible -> add the co
   const WaveDev& w;
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
     s.slot = i;
-    trav_init(s, w.sh_o[i], w.sh_d[i]);
+    trav_init(s, w.scene, w.sh_o[i], w.sh_d[i]);
   }
   __device__ __forceinline__ void store(const TravState& s) const {
     if (s.hit_id >= 0) return;  // occluded (render.glsl:122)
@@ -194,12 +194,13 @@ struct ShadowIO {  // any hit over the dense shadow queue; visible -> add the co
 };
 // Standalone ray batch (hjk_trace_first_hit): rays and results are indexed by ray number.
 struct BatchIO {
+  const SceneDev& sc;
   const f4* ray_o;
   const f4* ray_d;
   f4* hit;
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
     s.slot = i;
-    trav_init(s, ray_o[i], ray_d[i]);
+    trav_init(s, sc, ray_o[i], ray_d[i]);
   }
   __device__ __forceinline__ void store(const TravState& s) const {
     hit[s.slot] = F4(__int_as_float(s.hit_id), s.hit_t, s.hit_u, s.hit_v);
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(kTravThreads) k_shadow(WaveDev w, uint32_t bou
 template <bool ANY_HIT>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
                                                               f4* hit, uint32_t n, uint32_t* cursor, float eps) {
-  const BatchIO io{ray_o, ray_d, hit};
+  const BatchIO io{sc, ray_o, ray_d, hit};
   traverse_queue<ANY_HIT>(sc, io, n, cursor, eps);
 }
 

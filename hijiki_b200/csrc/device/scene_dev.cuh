@@ -56,6 +56,10 @@ struct SceneDev {
   const f4* emissive;
   uint32_t num_spheres, num_quads, num_triangles, num_emitters;
   HjkCamera camera;
+  // bounding ball of the sphere CENTRES (xyz, radius) and the sphere radius range: inputs of the
+  // traversal's sphere guard (traverse.cuh)
+  float sph_centre[4];
+  float sph_rmin, sph_rmax;
 };
 
 }  // namespace hjk

@@ -52,6 +52,9 @@ struct TravState {
   int32_t hit_id;        // global shape id of the current winner, -1 = none
   float hit_t, hit_u, hit_v;
   uint32_t slot;         // caller payload (path slot / ray index)
+  // sphere guard (see trav_init): per-axis box inflation in t units, box-test interval
+  float infl_x, infl_y, infl_z;
+  float box_tmin, box_tmax_scale;
 };
 
 HJK_HD float safe_rcp(float d) {
@@ -60,10 +63,43 @@ HJK_HD float safe_rcp(float d) {
   return 1.0f / d;
 }
 
-HJK_HD void trav_init(TravState& s, const f4& o_tmin, const f4& d_tmax) {
+// SPHERE GUARD.  The reference's sphere test (shapes/sphere.glsl:18-41) solves t^2 + b t + c = 0,
+// i.e. it assumes |direction| = 1.  Directions drift off unit length along specular chains
+// (n = (p - centre)/r is not exactly unit, reflect() amplifies it), and for s^2 = |d|^2 != 1 the
+// test is no longer geometric: it accepts exactly the rays whose line passes within
+//     R'^2 = r^2/s^2 + L^2 (1 - 1/s^2)          (L = |origin - centre|)
+// of the centre, and reports t' = s^2 * (true entry parameter of that ball).  To stay a superset
+// of what the reference accepts, boxes are inflated per ray by Delta >= R' - r and the box
+// interval is [0, tMax * max(1, 1/s^2)].  For |s^2 - 1| of a few ulps this degenerates to a
+// pad of ~1e-7 L^2 / r; for scenes without spheres it is switched off (triangle and quad tests
+// are homogeneous in d, hence geometric for any s).
+HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const f4& d_tmax) {
   s.ox = o_tmin.x, s.oy = o_tmin.y, s.oz = o_tmin.z, s.tmin = o_tmin.w;
   s.dx = d_tmax.x, s.dy = d_tmax.y, s.dz = d_tmax.z, s.tmax = d_tmax.w;
   s.idx = safe_rcp(s.dx), s.idy = safe_rcp(s.dy), s.idz = safe_rcp(s.dz);
+  s.infl_x = s.infl_y = s.infl_z = 0.f;
+  s.box_tmin = s.tmin;
+  s.box_tmax_scale = 1.0f;
+  if (sc.num_spheres) {
+    const float s2 = s.dx * s.dx + s.dy * s.dy + s.dz * s.dz;
+    const float lx = s.ox - sc.sph_centre[0], ly = s.oy - sc.sph_centre[1], lz = s.oz - sc.sph_centre[2];
+    const float L = sqrtf(lx * lx + ly * ly + lz * lz) + sc.sph_centre[3];
+    const float inv_s2 = 1.0f / s2;
+    float delta;
+    if (s2 >= 1.0f) {
+      delta = sqrtf(sc.sph_rmin * sc.sph_rmin + L * L * (1.0f - inv_s2)) - sc.sph_rmin;
+    } else {
+      delta = sc.sph_rmax * (sqrtf(inv_s2) - 1.0f);
+    }
+    delta = delta * 1.02f + 1e-6f * (L + 1.0f);
+    if (!(delta >= 0.f)) delta = x::as_float(0x7F800000u);  // NaN / degenerate direction: no culling
+    const float ax = s.idx < 0.f ? -s.idx : s.idx, ay = s.idy < 0.f ? -s.idy : s.idy,
+                az = s.idz < 0.f ? -s.idz : s.idz;
+    s.infl_x = delta * ax, s.infl_y = delta * ay, s.infl_z = delta * az;
+    s.box_tmin = 0.f;
+    s.box_tmax_scale = (inv_s2 > 1.0f ? inv_s2 : 1.0f) * 1.000001f;
+    if (!(s.box_tmax_scale >= 1.0f)) s.box_tmax_scale = x::as_float(0x7F800000u);
+  }
   const uint32_t oct = (s.idx < 0.f ? 1u : 0u) | (s.idy < 0.f ? 2u : 0u) | (s.idz < 0.f ? 4u : 0u);
   s.octinv4 = (7u - oct) * 0x01010101u;
   s.ng_x = 0;
@@ -84,6 +120,10 @@ HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, c
   const float orgx = (q0.x - s.ox) * s.idx;
   const float orgy = (q0.y - s.oy) * s.idy;
   const float orgz = (q0.z - s.oz) * s.idz;
+  // near planes move towards the origin, far planes away from it, by the sphere-guard inflation
+  const float o0x = orgx - s.infl_x, o0y = orgy - s.infl_y, o0z = orgz - s.infl_z;
+  const float o1x = orgx + s.infl_x, o1y = orgy + s.infl_y, o1z = orgz + s.infl_z;
+  const float box_tmax = s.tmax * s.box_tmax_scale;
   const bool nx = s.idx < 0.f, ny = s.idy < 0.f, nz = s.idz < 0.f;
   uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
@@ -105,14 +145,14 @@ HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, c
 #pragma unroll
 #endif
     for (int j = 0; j < 4; j++) {
-      const float t0x = fmaf(byte_to_float(nearx, j), adjx, orgx);
-      const float t0y = fmaf(byte_to_float(neary, j), adjy, orgy);
-      const float t0z = fmaf(byte_to_float(nearz, j), adjz, orgz);
-      const float t1x = fmaf(byte_to_float(farx, j), adjx, orgx);
-      const float t1y = fmaf(byte_to_float(fary, j), adjy, orgy);
-      const float t1z = fmaf(byte_to_float(farz, j), adjz, orgz);
-      const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.tmin));
-      const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, s.tmax));
+      const float t0x = fmaf(byte_to_float(nearx, j), adjx, o0x);
+      const float t0y = fmaf(byte_to_float(neary, j), adjy, o0y);
+      const float t0z = fmaf(byte_to_float(nearz, j), adjz, o0z);
+      const float t1x = fmaf(byte_to_float(farx, j), adjx, o1x);
+      const float t1y = fmaf(byte_to_float(fary, j), adjy, o1y);
+      const float t1z = fmaf(byte_to_float(farz, j), adjz, o1z);
+      const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.box_tmin));
+      const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, box_tmax));
       if (cmin <= cmax) {
         const uint32_t bits = (child_bits4 >> (8 * j)) & 0xFFu;
         const uint32_t index = (bit_index4 >> (8 * j)) & 0xFFu;

@@ -503,6 +503,26 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
     out.nodes[cur.wide] = wn;
   }
   out.n_shapes = n;
+  if (S) {
+    const HjkSphere* sp = (const HjkSphere*)s.spheres.ptr;
+    Box cb;
+    cb.reset();
+    float rmin = kInf, rmax = 0.f;
+    for (uint64_t i = 0; i < S; i++) {
+      cb.grow(sp[i].position);
+      rmin = std::min(rmin, std::fabs(sp[i].radius));
+      rmax = std::max(rmax, std::fabs(sp[i].radius));
+    }
+    float rad2 = 0.f;
+    for (int k = 0; k < 3; k++) {
+      out.sph_centre[k] = 0.5f * (cb.lo[k] + cb.hi[k]);
+      const float h = 0.5f * (cb.hi[k] - cb.lo[k]);
+      rad2 += h * h;
+    }
+    out.sph_centre[3] = std::sqrt(rad2) * 1.0001f;
+    out.sph_rmin = rmin;
+    out.sph_rmax = rmax;
+  }
   return true;
 }
 

@@ -16,6 +16,9 @@ struct WideBvh {
   float sah_cost = 0.f;  // collapse cost of the root, relative to the root area
   uint32_t depth = 0;
   uint32_t n_shapes = 0;
+  // bounding ball of the sphere centres and radius range (sphere guard of the traversal)
+  float sph_centre[4] = {0, 0, 0, 0};
+  float sph_rmin = 0.f, sph_rmax = 0.f;
 };
 
 // default relative pad (times the larger of scene extent and |coordinate|)

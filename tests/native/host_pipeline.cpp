@@ -96,6 +96,8 @@ void* ht_create(const HjkScene* s, float pad_rel, char* err_out, int err_cap) {
   sc.num_triangles = info->num_triangles;
   sc.num_emitters = info->num_emitters;
   sc.camera = info->camera;
+  for (int k = 0; k < 4; k++) sc.sph_centre[k] = h->bvh.sph_centre[k];
+  sc.sph_rmin = h->bvh.sph_rmin, sc.sph_rmax = h->bvh.sph_rmax;
   return h;
 }
 void ht_destroy(void* p) { delete (Harness*)p; }
@@ -117,7 +119,7 @@ void ht_trace(void* p, const HjkRay* rays, uint64_t n, int any_hit, float eps, i
   Harness* h = (Harness*)p;
   for (uint64_t i = 0; i < n; i++) {
     TravState s;
-    trav_init(s, F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min),
+    trav_init(s, h->sc, F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min),
               F4(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2], rays[i].t_max));
     HostStack st;
     auto never = []() { return false; };
@@ -187,7 +189,7 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
           in.bounce = bounce;
           // extend
           TravState s;
-          trav_init(s, in.ray_o, in.ray_d);
+          trav_init(s, h->sc, in.ray_o, in.ray_d);
           HostStack st;
           auto never = []() { return false; };
           n_ext++;
@@ -205,7 +207,7 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
           if (o.has_shadow) {
             n_sh++;
             TravState ss;
-            trav_init(ss, o.sh_o, o.sh_d);
+            trav_init(ss, h->sc, o.sh_o, o.sh_d);
             HostStack st2;
             trav_run<true>(h->sc, ss, st2, prm->eps, never);
             if (ss.hit_id < 0) {
@@ -239,6 +241,55 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
   if (layers_out) memcpy(layers_out, layers.data(), layers.size() * 4);
   if (counts) counts[0] = n_paths, counts[1] = n_ext, counts[2] = n_sh;
   return 0;
+}
+
+// One pixel's path, bounce by bounce (debugging aid, mirrors orc_trace_path): out = (shape id, t bits,
+// rng after, shadow state) per vertex.
+int ht_trace_path(void* p, const HjkImageBlock* blk, uint32_t lx, uint32_t ly, const HjkParams* prm, int32_t* out,
+                  int capacity, float* rays_out) {
+  Harness* h = (Harness*)p;
+  VertexIn in;
+  const uint32_t gx = lx + blk->origin[0], gy = ly + blk->origin[1];
+  in.rng = seed_rng(blk->seed + lx + ly * blk->dimension[0]);
+  camera_ray(h->sc.camera, x::add((float)gx, blk->sample_offset[0]), x::add((float)gy, blk->sample_offset[1]),
+             (float)blk->original_dimension[0], (float)blk->original_dimension[1], prm->eps, in.ray_o, in.ray_d);
+  in.throughput = V3(1.f);
+  in.extinction = V3(0.f);
+  in.was_discrete = true;
+  int n = 0;
+  auto never = []() { return false; };
+  for (uint32_t bounce = 0; bounce < prm->max_bounces && n < capacity; bounce++) {
+    in.bounce = bounce;
+    if (rays_out) {
+      memcpy(rays_out + 8 * n, &in.ray_o, 16);
+      memcpy(rays_out + 8 * n + 4, &in.ray_d, 16);
+    }
+    TravState s;
+    trav_init(s, h->sc, in.ray_o, in.ray_d);
+    HostStack st;
+    trav_run<false>(h->sc, s, st, prm->eps, never);
+    int32_t* o = out + 4 * n++;
+    o[0] = s.hit_id;
+    memcpy(&o[1], &s.hit_t, 4);
+    o[2] = 0, o[3] = 0;
+    if (s.hit_id < 0) break;
+    in.hit_id = s.hit_id, in.hit_t = s.hit_t, in.hit_u = s.hit_u, in.hit_v = s.hit_v;
+    VertexOut vo;
+    shade_vertex(h->sc, in, prm->max_bounces, prm->rr_start, prm->eps, vo);
+    o[2] = (int32_t)vo.rng;
+    if (vo.has_shadow) {
+      TravState ss;
+      trav_init(ss, h->sc, vo.sh_o, vo.sh_d);
+      HostStack st2;
+      trav_run<true>(h->sc, ss, st2, prm->eps, never);
+      o[3] = ss.hit_id < 0 ? 2 : 1;
+    }
+    if (!vo.continues) break;
+    in.ray_o = vo.next_o, in.ray_d = vo.next_d;
+    in.throughput = vo.throughput, in.extinction = vo.extinction;
+    in.rng = vo.rng, in.was_discrete = vo.was_discrete;
+  }
+  return n;
 }
 
 // reconstruction of caller-supplied layers (hjk_denoise_pass semantics)
