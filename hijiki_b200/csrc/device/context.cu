@@ -92,7 +92,8 @@ struct HjkContext {
   std::vector<int> ev_slot;
   size_t ev_used = 0;
   int n_sms = 0;
-  int blocks_trav = 0, blocks_tile = 0;  // resident CTAs per SM of the persistent kernels
+  int blocks_trav = 0, blocks_tile = 0;  // resident CTAs per SM of the persistent kernels (traverse / shade)
+  int blocks_light = 0;                  // ... of the light tile kernels (raygen, bin)
   std::string error;
   bool profiling = false;
   uint64_t wave_paths = 4u << 20;  // target camera paths per wave
@@ -320,6 +321,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.has_extinction = c->has_extinction ? 1u : 0u;
 
   const int g_trav = grid_for(c, c->blocks_trav), g_tile = grid_for(c, c->blocks_tile);
+  const int g_light = grid_for(c, c->blocks_light);
   uint64_t n_ext = 0, n_sh = 0, n_paths = 0;
   c->h_counters.resize(n_ctr);
   // with the reference's bounce limit (1000) paths die by roulette long before the limit:
@@ -334,7 +336,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     HJK_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, n_ctr * 4, c->stream));
     {
       KernelTimer t(c, stats, HJK_K_RAYGEN);
-      k_raygen<<<g_tile, kTileThreads, 0, c->stream>>>(w);
+      k_raygen<<<g_light, kTileThreads, 0, c->stream>>>(w);
       launches++;
     }
     uint32_t bounces_run = 0;
@@ -345,7 +347,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       }
       {
         KernelTimer t(c, stats, HJK_K_SORT);
-        k_bin<<<g_tile, kTileThreads, 0, c->stream>>>(w, b);
+        k_bin<<<g_light, kTileThreads, 0, c->stream>>>(w, b);
       }
       {
         KernelTimer t(c, stats, HJK_K_SHADE);
@@ -461,6 +463,8 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   c->blocks_trav = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
   c->blocks_tile = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bin, kTileThreads, 0);
+  c->blocks_light = std::max(occ, 1);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail("kernel image (built for sm_100a)", e);
   *out_ctx = c;
   return HJK_OK;

@@ -116,9 +116,9 @@ def test_render_accumulator_matches_oracle(gpu_ctx, kind, max_bounces, use_bvh, 
           f"{st.n_extension_rays}+{st.n_shadow_rays} oracle {ost.n_extension_rays}+{ost.n_shadow_rays}")
     assert st.n_paths == ost.n_paths == w * h * spp
     assert diff.sum() <= 25 * 4
-    if diff.sum() == 0:
-        assert st.n_extension_rays == ost.n_extension_rays and st.n_shadow_rays == ost.n_shadow_rays
+    # tie-affected paths may take a different number of bounces
     assert abs(st.n_extension_rays - ost.n_extension_rays) <= 100
+    assert abs(st.n_shadow_rays - ost.n_shadow_rays) <= 100
     img = gpu_ctx.readback(normalise=True)
     ref = acc_o[..., :3] / acc_o[..., 3:4]
     same = ~diff

@@ -127,8 +127,7 @@ def test_render_accumulator_matches_oracle(oracle, hosttest, request, which, max
     assert cnt[0] == st.n_paths == 136 * 100 * 2
     diff = (acc_o.view(np.uint32) != acc_h.view(np.uint32)).any(axis=2)
     assert diff.sum() <= 25 * 2  # at most two tie-affected samples (each touches <= 25 texels)
-    if diff.sum() == 0:
-        assert cnt[1] == st.n_extension_rays and cnt[2] == st.n_shadow_rays
+    assert abs(int(cnt[1]) - int(st.n_extension_rays)) <= 20 and abs(int(cnt[2]) - int(st.n_shadow_rays)) <= 20
     assert np.isfinite(acc_h).all() and acc_h[..., 3].min() > 0
 
 
