@@ -1,25 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — Mrays/s (all bounces) of the path-tracing hot path on BASELINE.json's config 2
-(scenes/cbox, 1920x1080, 1024 spp, max 8 bounces), plus the reconstruction ("denoiser") HBM GB/s.
+"""bench.py — Mrays/s (all bounces) of the path-tracing hot path, plus the reconstruction
+("denoiser") HBM GB/s.  Default workload: BASELINE.json configs[1] (scenes/cbox, 1920x1080,
+1024 spp, max 8 bounces).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
-One STEP = `--spp-per-step` consecutive sample passes of the 1024-spp job on every rank (a
-slice of the job's own block list: 135 ImageBlocks per pass), integrated, reconstructed into the
-accumulator and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectScene call
+One STEP = one frame of `--spp-per-step` consecutive sample passes of the job on every rank (a
+slice of the job's own ImageBlock list): accumulator zeroed, passes integrated and reconstructed
+into it and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectScene call
 (reference shader/render.glsl:94,122): extension + shadow rays.
 
   value      device-resident throughput: the step's block list already lives in HBM; timed with
              CUDA events on the stream the kernels run on, max over ranks.
   e2e        the same step through the public call (`hjk_render` with a HOST block list in pinned
-             memory + `hjk_readback` of the accumulator to pinned host memory), copies in the timed
-             region.
+             memory + `hjk_readback` of the normalised frame to pinned host memory), copies in the
+             timed region.
   roofline   the dominant kernel (k_extend, closest-hit BVH traversal): algorithmic bytes it must
              move per ray / its average launch time, against the measured HBM copy peak.
   cpu_baseline / --impl reference
              the CPU restatement of the reference GLSL (oracle/, threaded-BVH2 mode = the
              reference's --use-bvh), on all host cores, on a bounded sample of the same workload.
              The reference's own wgpu/lavapipe path cannot run in this image.
+
+Other workloads (`--workload`): cbox_default (configs[0]), terrain (configs[2], 10 M triangles),
+spheres (configs[3], 512 dielectric/mirror spheres at 3840x2160); configs[4] (reconstruction on
+3840x2160 feature buffers) is the `denoiser` object of every line.
 """
 from __future__ import annotations
 
@@ -37,9 +42,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH, HEIGHT, SPP, MAX_BOUNCES, BLOCK = 1920, 1080, 1024, 8, 128
+BLOCK = 128
 CBOX = os.path.join(ROOT, "scenes", "cbox", "cbox.obj")
-WORKLOAD = "scenes/cbox 1920x1080, 1024 spp, max 8 bounces (BASELINE.json configs[1])"
+# name -> (label, scene kind, width, height, spp, max_bounces, default spp per step)
+WORKLOADS = {
+    "cbox1080": ("scenes/cbox 1920x1080, 1024 spp, max 8 bounces (BASELINE.json configs[1])", "cbox", 1920, 1080, 1024, 8, 32),
+    "cbox_default": ("scenes/cbox 800x600, 64 spp, max 1000 bounces, reference defaults (BASELINE.json configs[0])", "cbox", 800, 600, 64, 1000, 64),
+    "terrain": ("synthetic 10,008,370-triangle checkerboard terrain + emissive quads, 1920x1080, 64 spp, max 8 bounces (BASELINE.json configs[2])", "terrain", 1920, 1080, 64, 8, 8),
+    "spheres": ("synthetic 512-sphere dielectric/mirror lattice, 3840x2160, 4096 spp, max 8 bounces (BASELINE.json configs[3])", "spheres", 3840, 2160, 4096, 8, 4),
+}
 # algorithmic bytes: what k_extend itself must move per ray, and the whole
 # pipeline's per-ray queue traffic of SURVEY.md §8(d)
 EXTEND_BYTES_PER_RAY = 4 + 32 + 16
@@ -67,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.device)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -86,11 +97,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
             except Exception:
                 continue
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
@@ -98,13 +110,18 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def job_blocks():
+def make_scene(kind: str):
     import hijiki_b200 as hj
-    gen = hj.ImageBlockGenerator(WIDTH, HEIGHT, BLOCK, SPP)
-    return gen, gen.blocks()
+    if kind == "cbox":
+        return hj.Scene.from_obj(CBOX)
+    if kind == "terrain":
+        return hj.Scene.terrain(2237)
+    if kind == "spheres":
+        return hj.Scene.spheres(8)
+    raise KeyError(kind)
 
 
 def step_slice(blocks, bpp, step, rank, world, spp_per_step):
@@ -117,22 +134,21 @@ def step_slice(blocks, bpp, step, rank, world, spp_per_step):
     return np.ascontiguousarray(blocks[np.concatenate(idx)])
 
 
-# ------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank):
-    """The reference's algorithm on the host CPU (oracle port, all cores)."""
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------ CPU arm
+def _oracle_setup(wl):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _libs
     import hijiki_b200 as hj
-
+    label, kind, width, height, spp, max_bounces, _ = wl
     O = _libs.oracle()
     cores = O.orc_hardware_threads()
-    compiled = hj.Scene.from_obj(CBOX).compile(use_bvh=True)
-    gen, blocks = job_blocks()
-    bpp = gen.blocks_per_pass
-    op = _libs.orc_params(max_bounces=MAX_BOUNCES, use_bvh=1, block_size=BLOCK)
-    acc = np.zeros((HEIGHT, WIDTH, 4), np.float32)
+    compiled = make_scene(kind).compile(use_bvh=True)
+    gen = hj.ImageBlockGenerator(width, height, BLOCK, spp)
+    # bounded block list: never materialise millions of blocks for the CPU arm
+    gen.num_samples = min(spp, 64)
+    blocks = gen.blocks()
+    op = _libs.orc_params(max_bounces=max_bounces, use_bvh=1, block_size=BLOCK)
+    acc = np.zeros((height, width, 4), np.float32)
 
     def run(sample):
         st = _libs.OrcStats()
@@ -143,55 +159,63 @@ def run_reference(args, rank):
         assert rc == 0
         return st.n_extension_rays + st.n_shadow_rays, dt
 
-    # calibrate on two blocks, then size a step so the whole run stays within ~100 s
-    rays, dt = run(blocks[60:62])
-    per_block = max(dt / 2, 1e-3)
-    budget = 100.0 / max(args.steps + args.warmup, 1)
-    nb = int(min(32 * bpp, max(2, budget / per_block)))
-    n_total = len(blocks)
+    return run, blocks, gen.blocks_per_pass, cores
+
+
+def run_reference(args, rank, wl):
+    """The reference's algorithm on the host CPU (oracle port, all cores)."""
+    if rank != 0:
+        return
+    label, kind, width, height = wl[:4]
+    base = {"impl": "reference", "metric": "Mrays/s (all bounces)", "unit": "Mrays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if kind == "terrain":
+        base["unavailable"] = ("the reference's flattened BVH uses exit index 1000000 as its end sentinel "
+                               "(src/main.rs:231) and cannot represent a 10 M-triangle scene")
+        print(json.dumps(base), flush=True)
+        return
+    run, blocks, bpp, cores = _oracle_setup(wl)
+    mid = bpp // 2
+    _, dt = run(blocks[mid:mid + 2])  # calibrate on two blocks from the middle of the frame
+    per_block = max(dt / 2, 1e-4)
+    budget = args.cpu_seconds / max(args.steps + args.warmup, 1)
+    nb = int(min(len(blocks) // 2, max(2, budget / per_block)))
     for w in range(args.warmup):
-        run(blocks[(w * nb) % (n_total - nb):][:nb])
+        run(blocks[(w * nb) % (len(blocks) - nb):][:nb])
     tot_rays, tot_dt = 0, 0.0
     for k in range(args.steps):
-        first = ((args.warmup + k) * nb) % (n_total - nb)
+        first = ((args.warmup + k) * nb) % (len(blocks) - nb)
         r, dt = run(blocks[first:first + nb])
         tot_rays += r
         tot_dt += dt
     value = tot_rays / tot_dt / 1e6
-    sample = f"{nb} ImageBlocks ({nb / bpp:.1f} sample passes of 1920x1080) per step"
-    line = {
-        "impl": "reference", "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of reference GLSL (threaded-BVH2 mode), "
-                   f"{cores} cores — the reference's wgpu/lavapipe path cannot run in this image"},
+    sample = f"{nb} ImageBlocks ({nb / bpp:.2f} sample passes of {width}x{height}) per step"
+    base.update({
+        "value": value, "ms_per_step": tot_dt / args.steps * 1e3,
+        "config": {"workload": label, "note": "CPU restatement of reference GLSL (threaded-BVH2 mode = reference "
+                   f"--use-bvh), {cores} host threads — the reference's wgpu/lavapipe path cannot run in this image"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+    })
+    print(json.dumps(base), flush=True)
 
 
-def cpu_baseline_sample(compiled, blocks, bpp):
-    """Bounded CPU sample for the main line (rank 0, N = 1): ~10-20 s of oracle work."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import _libs
-    O = _libs.oracle()
-    cores = O.orc_hardware_threads()
-    op = _libs.orc_params(max_bounces=MAX_BOUNCES, use_bvh=1, block_size=BLOCK)
-    acc = np.zeros((HEIGHT, WIDTH, 4), np.float32)
-    st = _libs.OrcStats()
-    t0 = time.perf_counter()
-    O.orc_render(C.byref(compiled.view), _libs.ptr(blocks[60:62]), 2, C.byref(op), _libs.ptr(acc), C.byref(st), cores)
-    per_block = max((time.perf_counter() - t0) / 2, 1e-4)
-    nb = int(min(len(blocks), max(2, 15.0 / per_block)))  # ~15 s of CPU work
-    st = _libs.OrcStats()
-    t0 = time.perf_counter()
-    O.orc_render(C.byref(compiled.view), _libs.ptr(blocks[:nb]), nb, C.byref(op), _libs.ptr(acc), C.byref(st), cores)
-    dt = time.perf_counter() - t0
-    rays = st.n_extension_rays + st.n_shadow_rays
+def cpu_baseline_sample(wl):
+    """Bounded CPU sample for the main line (rank 0, N = 1): ~15 s of oracle work."""
+    label, kind, width, height = wl[:4]
+    if kind == "terrain":
+        return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port",
+                "sample": "unavailable: the reference BVH layout cannot represent 10 M triangles (src/main.rs:231)"}
+    run, blocks, bpp, cores = _oracle_setup(wl)
+    mid = bpp // 2
+    _, dt = run(blocks[mid:mid + 2])
+    per_block = max(dt / 2, 1e-4)
+    nb = int(min(len(blocks), max(2, 15.0 / per_block)))
+    rays, dt = run(blocks[:nb])
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-            "sample": f"first {nb} ImageBlocks ({nb / bpp:.1f} sample passes of 1920x1080) of the job, "
+            "sample": f"first {nb} ImageBlocks ({nb / bpp:.1f} sample passes of {width}x{height}) of the job, "
                       f"{rays / 1e6:.1f} Mrays in {dt:.1f} s (oracle, threaded-BVH2 mode = reference --use-bvh)"}
 
 
@@ -202,18 +226,24 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=32)
+    ap.add_argument("--workload", default="cbox1080", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-denoiser", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=100.0, help="wall budget of the --impl reference run")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    label, kind, width, height, spp, max_bounces, default_sps = wl
+    sps = args.spp_per_step or default_sps
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, wl)
         return
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -225,17 +255,24 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    gen, blocks = job_blocks()
+    n_steps_total = args.warmup + args.steps
+    gen = hj.ImageBlockGenerator(width, height, BLOCK, spp)
     bpp = gen.blocks_per_pass
-    compiled = hj.Scene.from_obj(CBOX).compile(use_bvh=True)
+    # only the passes the run touches are generated (the list is a prefix of the job's list)
+    gen.num_samples = min(spp, n_steps_total * sps * world)
+    blocks = gen.blocks()
+    t0 = time.perf_counter()
+    compiled = make_scene(kind).compile(use_bvh=False)
+    t_scene = time.perf_counter() - t0
     ctx = hj.Context(local_rank)
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
     ctx.scene_upload(compiled)
-    ctx.frame_begin(WIDTH, HEIGHT)
+    t_upload = time.perf_counter() - t0
+    ctx.frame_begin(width, height)
     ctx.set_profiling(True)
-    params = hj.make_params(max_bounces=MAX_BOUNCES)
-    n_steps_total = args.warmup + args.steps
+    params = hj.make_params(max_bounces=max_bounces)
 
     # accumulator as a torch tensor (no copy) so torch.distributed can reduce it in place
     acc_ptr, acc_n = ctx.accumulator_device_ptr()
@@ -256,9 +293,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm: block lists uploaded before the timed region
-    slices = [step_slice(blocks, bpp, s, rank, world, args.spp_per_step) for s in range(n_steps_total)]
+    slices = [step_slice(blocks, bpp, s, rank, world, sps) for s in range(n_steps_total)]
     handles = [ctx.blocks_upload(s) for s in slices]
     for s in range(args.warmup):
+        ctx.frame_begin(width, height)
         ctx.render_resident(handles[s], 0, slices[s].size, params)
         allreduce()
     barrier()
@@ -269,6 +307,7 @@ def main():
     kernel_ms = {}
     ev0.record(stream)
     for s in range(args.warmup, n_steps_total):
+        ctx.frame_begin(width, height)
         st = ctx.render_resident(handles[s], 0, slices[s].size, params)
         allreduce()
         rays += st.n_rays
@@ -284,32 +323,40 @@ def main():
     for h in handles:
         ctx.blocks_free(h)
 
-    # ---------------- end-to-end arm: host block list in, accumulator out, every step
-    pinned_blocks = [torch.from_numpy(s.view(np.uint8).copy()).pin_memory() for s in slices]
-    out_host = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
-    for s in range(args.warmup):
-        ctx.render((pinned_blocks[s].data_ptr(), slices[s].size), params)
-        allreduce()
-        ctx.readback_ptr(out_host.data_ptr(), WIDTH * 16, normalise=True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_rays = 0
-    e0.record(stream)
-    for s in range(args.warmup, n_steps_total):
-        st = ctx.render((pinned_blocks[s].data_ptr(), slices[s].size), params)
-        allreduce()
-        ctx.readback_ptr(out_host.data_ptr(), WIDTH * 16, normalise=True)
-        e2e_rays += st.n_rays
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    result_mean = float(out_host[..., :3].mean())
+    # ---------------- end-to-end arm: host block list in, normalised frame out, every step
+    e2e_ms, e2e_rays, result_mean = None, 0, None
+    if not args.no_e2e:
+        pinned_blocks = [torch.from_numpy(s.view(np.uint8).copy()).pin_memory() for s in slices]
+        out_host = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
 
-    # ---------------- reconstruction ("denoiser") bandwidth on 3840x2160 feature buffers (config 5)
+        def e2e_step(s):
+            ctx.frame_begin(width, height)
+            st = ctx.render((pinned_blocks[s].data_ptr(), slices[s].size), params)
+            allreduce()
+            ctx.readback_ptr(out_host.data_ptr(), width * 16, normalise=True)
+            return st.n_rays
+
+        for s in range(args.warmup):
+            e2e_step(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(args.warmup, n_steps_total):
+            e2e_rays += e2e_step(s)
+        e1.record(stream)
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        result_mean = float(out_host[..., :3].mean())
+
+    info = {k: ctx.get_info(k) for k in ("bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "wave_paths",
+                                          "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_sms")}
+    ctx.close()
+
+    # ---------------- reconstruction ("denoiser") bandwidth on 3840x2160 feature buffers (configs[4])
     denoiser = None
     if not args.no_denoiser:
         dw, dh = 3840, 2160
-        rng = np.random.default_rng(5)
+        rng = np.random.default_rng(5 + rank)
         rad = np.exp(rng.standard_normal((dh, dw, 4), dtype=np.float32))
         rad[..., 3] = 1.0
         nrm = rng.standard_normal((dh, dw, 4), dtype=np.float32)
@@ -322,37 +369,39 @@ def main():
         reps = 50
         dms = dctx.denoise_resident(params, reps)
         gbs = RECON_BYTES_PER_PX * dw * dh * reps / (dms * 1e-3) / 1e9
-        denoiser = {"workload": "3840x2160 synthetic feature buffers, 510 ImageBlocks/pass, R=2", "ms_per_pass": dms / reps,
-                    "bytes_per_px": RECON_BYTES_PER_PX, "achieved": gbs, "unit": "GB/s"}
+        denoiser = {"workload": "3840x2160 synthetic feature buffers (random unit normals), 510 ImageBlocks/pass, R=2 "
+                                "(BASELINE.json configs[4]), per GPU",
+                    "ms_per_pass": dms / reps, "bytes_per_px": RECON_BYTES_PER_PX, "achieved": gbs, "unit": "GB/s"}
         dctx.close()
 
     # ---------------- gather over ranks (max time, summed rays)
     peak, peak_src = measured_peaks()
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms = float(t[0]), (float(t[1]) if e2e_ms is not None else None)
         c = torch.tensor([rays, e2e_rays, ext_rays, sh_rays, launches], dtype=torch.float64, device="cuda")
         dist.all_reduce(c)
         rays, e2e_rays, ext_rays, sh_rays, launches = (int(v) for v in c.tolist())
     if rank == 0:
         value = rays / (ms * 1e-3) / 1e6
-        e2e = e2e_rays / (e2e_ms * 1e-3) / 1e6
-        n_ext_launches = args.steps * MAX_BOUNCES * max(1, -(-args.spp_per_step // max(1, round((4 << 20) / (WIDTH * HEIGHT)))))
+        wave_passes = max(1, min(sps, (info["wave_paths"] + width * height // 2) // (width * height)))
+        n_ext_launches = args.steps * max_bounces * -(-sps // wave_passes)
         ext_ms = kernel_ms.get("extend", 0.0)
         ext_local = ext_rays // world
         achieved = EXTEND_BYTES_PER_RAY * ext_local / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
+        pipe = (PIPE_BYTES_EXT * ext_rays + PIPE_BYTES_SHADOW * sh_rays) / world / (ms * 1e-3) / 1e9
         line = {
             "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "spp_per_step_per_gpu": args.spp_per_step,
-                       "blocks_per_step_per_gpu": args.spp_per_step * bpp, "parallelism": f"sample-pass dp{world}",
-                       "l2": "per-step working set (path state + queues of a 4M-path wave, ~0.7 GB) exceeds the 126 MB L2",
-                       "image_mean": result_mean},
-            "rays": {"extension": ext_rays, "shadow": sh_rays, "per_path": rays / max(1, args.steps * args.spp_per_step * WIDTH * HEIGHT * world)},
-            "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": int(slices[0].nbytes),
-                    "d2h_bytes_per_step": WIDTH * HEIGHT * 16, "ms_per_step": e2e_ms / args.steps},
+            "config": {"workload": label, "spp_per_step_per_gpu": sps, "blocks_per_step_per_gpu": sps * bpp,
+                       "parallelism": f"sample-pass dp{world}",
+                       "l2": "inputs larger than L2: the path state + queues of one wave (~0.7 GB) exceed the 126 MB L2",
+                       "image_mean": result_mean, "bvh": info,
+                       "scene_build_s": round(t_scene, 2), "bvh_build_upload_s": round(t_upload, 2)},
+            "rays": {"extension": ext_rays, "shadow": sh_rays,
+                     "per_path": rays / max(1, args.steps * sps * width * height * world)},
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
             "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -360,17 +409,21 @@ def main():
                          "bytes_per_ray": EXTEND_BYTES_PER_RAY, "launches": n_ext_launches,
                          "avg_launch_ms": ext_ms / n_ext_launches if n_ext_launches else None,
                          "share_of_step": ext_ms / ms if ms else None,
-                         "note": "cbox (0.35 MB of BVH) is cache-resident: traversal is issue/latency-bound, not HBM-bound"},
-            "pipeline_bytes": {"achieved": (PIPE_BYTES_EXT * ext_rays + PIPE_BYTES_SHADOW * sh_rays) / world / (ms * 1e-3) / 1e9,
-                               "unit": "GB/s", "frac": (PIPE_BYTES_EXT * ext_rays + PIPE_BYTES_SHADOW * sh_rays) / world / (ms * 1e-3) / 1e9 / peak},
+                         "note": "traversal of a cache-resident BVH is issue/latency-bound, not HBM-bound "
+                                 "(SURVEY.md §8d); see profiles/ for SM issue utilisation"},
+            "pipeline_bytes": {"achieved": pipe, "unit": "GB/s", "frac": pipe / peak},
             "clocks": clocks,
         }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                           "h2d_bytes_per_step": int(slices[0].nbytes), "d2h_bytes_per_step": width * height * 16,
+                           "ms_per_step": e2e_ms / args.steps}
         if denoiser:
             denoiser["peak"] = peak
             denoiser["frac"] = denoiser["achieved"] / peak
             line["denoiser"] = denoiser
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample(compiled, blocks, bpp)
+            line["cpu_baseline"] = cpu_baseline_sample(wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
