@@ -15,8 +15,8 @@ into it and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectSce
   e2e        the same step through the public call (`hjk_render` with a HOST block list in pinned
              memory + `hjk_readback` of the normalised frame to pinned host memory), copies in the
              timed region.
-  roofline   the dominant kernel (k_extend, closest-hit BVH traversal): algorithmic bytes it must
-             move per ray / its average launch time, against the measured HBM copy peak.
+  roofline   the dominant kernel (k_trace, BVH traversal of extension + shadow rays): algorithmic
+             bytes it must move per ray / its average launch time, against the measured HBM copy peak.
   cpu_baseline / --impl reference
              the CPU restatement of the reference GLSL (oracle/, threaded-BVH2 mode = the
              reference's --use-bvh), on all host cores, on a bounded sample of the same workload.
@@ -51,9 +51,11 @@ WORKLOADS = {
     "terrain": ("synthetic 10,008,370-triangle checkerboard terrain + emissive quads, 1920x1080, 64 spp, max 8 bounces (BASELINE.json configs[2])", "terrain", 1920, 1080, 64, 8, 8),
     "spheres": ("synthetic 512-sphere dielectric/mirror lattice, 3840x2160, 4096 spp, max 8 bounces (BASELINE.json configs[3])", "spheres", 3840, 2160, 4096, 8, 4),
 }
-# algorithmic bytes: what k_extend itself must move per ray, and the whole
-# pipeline's per-ray queue traffic of SURVEY.md §8(d)
+# algorithmic bytes: what k_trace itself must move per ray (extension: queue entry +
+# ray in, hit record out; shadow: ray + payload in), and the whole pipeline's per-ray queue traffic
+# of SURVEY.md §8(d)
 EXTEND_BYTES_PER_RAY = 4 + 32 + 16
+SHADOW_BYTES_PER_RAY = 32 + 16
 PIPE_BYTES_EXT, PIPE_BYTES_SHADOW = 192, 96
 RECON_BYTES_PER_PX = 64  # 2 x 16 B layers + accumulator read + write (the all-zero albedo layer is elided)
 
@@ -386,10 +388,10 @@ def main():
     if rank == 0:
         value = rays / (ms * 1e-3) / 1e6
         wave_passes = max(1, min(sps, (info["wave_paths"] + width * height // 2) // (width * height)))
-        n_ext_launches = args.steps * max_bounces * -(-sps // wave_passes)
-        ext_ms = kernel_ms.get("extend", 0.0)
-        ext_local = ext_rays // world
-        achieved = EXTEND_BYTES_PER_RAY * ext_local / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
+        n_ext_launches = args.steps * (max_bounces + 1) * -(-sps // wave_passes)
+        ext_ms = kernel_ms.get("extend", 0.0)  # slot HJK_K_EXTEND times k_trace (extension + shadow rays)
+        trace_bytes = (EXTEND_BYTES_PER_RAY * ext_rays + SHADOW_BYTES_PER_RAY * sh_rays) / world
+        achieved = trace_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
         pipe = (PIPE_BYTES_EXT * ext_rays + PIPE_BYTES_SHADOW * sh_rays) / world / (ms * 1e-3) / 1e9
         line = {
             "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -404,9 +406,10 @@ def main():
                      "per_path": rays / max(1, args.steps * sps * width * height * world)},
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
-            "roofline": {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_ray": EXTEND_BYTES_PER_RAY, "launches": n_ext_launches,
+                         "bytes_per_ray": {"extension": EXTEND_BYTES_PER_RAY, "shadow": SHADOW_BYTES_PER_RAY},
+                         "launches": n_ext_launches,
                          "avg_launch_ms": ext_ms / n_ext_launches if n_ext_launches else None,
                          "share_of_step": ext_ms / ms if ms else None,
                          "note": "traversal of a cache-resident BVH is issue/latency-bound, not HBM-bound "

@@ -96,8 +96,9 @@ struct HjkContext {
   int blocks_light = 0;                  // ... of the light tile kernels (raygen, bin)
   std::string error;
   bool profiling = false;
-  uint64_t wave_paths = 4u << 20;  // target camera paths per wave
+  uint64_t wave_paths = 16u << 20;  // target camera paths per wave (2.7 GB of path state; tails amortise)
   float bvh_pad_rel = kDefaultBvhPadRel;
+  uint32_t fetch_threshold = kFetchThreshold, postpone_lanes = kPostponeLanes;
 
   // scene
   bool has_scene = false;
@@ -115,10 +116,12 @@ struct HjkContext {
 
   // wave buffers
   DevBuf<f4> d_ray_o, d_ray_d, d_hit, d_thr, d_ext, d_layer0, d_layer1, d_sh_o, d_sh_d, d_sh_c;
-  DevBuf<uint32_t> d_ext_q0, d_ext_q1, d_tag_q, d_counters;
+  DevBuf<uint32_t> d_ext_q0, d_ext_q1, d_counters;
+  DevBuf<unsigned long long> d_totals;  // paths, extension rays, shadow rays of the current call
   DevBuf<int32_t> d_tile_block;
   DevBuf<HjkImageBlock> d_blocks;
   DevBuf<float> d_weights;
+  DevBuf<uint32_t> d_taps;
   std::vector<uint32_t> h_counters;
   uint32_t last_wave_passes = 0;  // for hjk_read_intermediate
   bool have_features = false;
@@ -280,11 +283,13 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   HJK_CUDA(c, c->d_sh_c.ensure(n_slots));
   HJK_CUDA(c, c->d_ext_q0.ensure(n_slots));
   HJK_CUDA(c, c->d_ext_q1.ensure(n_slots));
-  HJK_CUDA(c, c->d_tag_q.ensure(n_slots * 5));
   const size_t n_ctr = ((size_t)prm->max_bounces + 1) * CTR_STRIDE;
   HJK_CUDA(c, c->d_counters.ensure(n_ctr));
+  HJK_CUDA(c, c->d_totals.ensure(3));
+  HJK_CUDA(c, cudaMemsetAsync(c->d_totals.p, 0, 3 * sizeof(unsigned long long), c->stream));
   HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
   HJK_CUDA(c, c->d_weights.ensure((size_t)n_blocks * taps * taps));
+  HJK_CUDA(c, c->d_taps.ensure((size_t)n_blocks * recon_tap_stride(R)));
   HJK_CUDA(c, cudaMemcpyAsync(c->d_tile_block.p, plan.tile_block.data(), plan.tile_block.size() * 4,
                               cudaMemcpyHostToDevice, c->stream));
 
@@ -297,8 +302,8 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   }
   if (do_recon) {
     KernelTimer t(c, stats, HJK_K_OTHER);
-    k_recon_weights<<<std::max<int>(1, (int)std::min<size_t>(1024, ((size_t)n_blocks * taps * taps + 255) / 256)), 256,
-                      0, c->stream>>>(d_blocks, (uint32_t)n_blocks, R, prm->recon_stddev, c->d_weights.p);
+    k_recon_weights<<<std::max<int>(1, (int)std::min<size_t>(1024, ((size_t)n_blocks + 127) / 128)), 128, 0,
+                      c->stream>>>(d_blocks, (uint32_t)n_blocks, R, prm->recon_stddev, c->d_weights.p, c->d_taps.p);
     launches++;
   }
 
@@ -311,7 +316,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.ray_o = c->d_ray_o.p, w.ray_d = c->d_ray_d.p, w.hit = c->d_hit.p, w.thr_rng = c->d_thr.p;
   w.extinction = c->d_ext.p;
   w.layer0 = c->d_layer0.p, w.layer1 = c->d_layer1.p;
-  w.ext_q[0] = c->d_ext_q0.p, w.ext_q[1] = c->d_ext_q1.p, w.tag_q = c->d_tag_q.p;
+  w.ext_q[0] = c->d_ext_q0.p, w.ext_q[1] = c->d_ext_q1.p;
   w.sh_o = c->d_sh_o.p, w.sh_d = c->d_sh_d.p, w.sh_c = c->d_sh_c.p;
   w.counters = c->d_counters.p;
   w.accumulator = c->d_acc.p;
@@ -319,9 +324,11 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.recon_radius = R;
   w.eps = prm->eps;
   w.has_extinction = c->has_extinction ? 1u : 0u;
+  w.fetch_threshold = c->fetch_threshold, w.postpone_lanes = c->postpone_lanes;
 
   const int g_trav = grid_for(c, c->blocks_trav), g_tile = grid_for(c, c->blocks_tile);
   const int g_light = grid_for(c, c->blocks_light);
+  const bool guard = c->scene.num_spheres != 0;
   uint64_t n_ext = 0, n_sh = 0, n_paths = 0;
   c->h_counters.resize(n_ctr);
   // with the reference's bounce limit (1000) paths die by roulette long before the limit:
@@ -339,34 +346,35 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       k_raygen<<<g_light, kTileThreads, 0, c->stream>>>(w);
       launches++;
     }
-    uint32_t bounces_run = 0;
-    for (uint32_t b = 0; b < prm->max_bounces; b++) {
+    // Extension rays exist for bounces [0, last).  Launch b traces them together with the shadow
+    // rays bounce b-1 emitted; one more launch after the last bounce drains its shadow rays.
+    uint32_t last = prm->max_bounces;
+    for (uint32_t b = 0;; b++) {
       {
         KernelTimer t(c, stats, HJK_K_EXTEND);
-        k_extend<<<g_trav, kTravThreads, 0, c->stream>>>(w, b);
+        if (guard)
+          k_trace<true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+        else
+          k_trace<false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+        launches++;
       }
-      {
-        KernelTimer t(c, stats, HJK_K_SORT);
-        k_bin<<<g_light, kTileThreads, 0, c->stream>>>(w, b);
-      }
+      if (b == last) break;
       {
         KernelTimer t(c, stats, HJK_K_SHADE);
         k_shade<<<g_tile, kTileThreads, 0, c->stream>>>(w, b);
       }
-      {
-        KernelTimer t(c, stats, HJK_K_SHADOW);
-        k_shadow<<<g_trav, kTravThreads, 0, c->stream>>>(w, b);
-      }
-      launches += 4;
-      bounces_run = b + 1;
-      if (b + 1 < prm->max_bounces && (b + 1) % check_every == 0) {
+      launches++;
+      if (b + 1 < last && (b + 1) % check_every == 0) {
         uint32_t live = 0;
         HJK_CUDA(c, cudaMemcpyAsync(&live, c->d_counters.p + (size_t)(b + 1) * CTR_STRIDE + CTR_EXT, 4,
                                     cudaMemcpyDeviceToHost, c->stream));
         HJK_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (live == 0) break;
+        if (live == 0) last = b + 1;
       }
     }
+    // fold this wave's ray counts into the call's totals on the device (no host sync per wave)
+    k_wave_totals<<<1, 32, 0, c->stream>>>(c->d_counters.p, prm->max_bounces + 1, c->d_totals.p);
+    launches++;
     HJK_CUDA(c, cudaGetLastError());
     if (do_recon) {
       KernelTimer t(c, stats, HJK_K_RECON);
@@ -376,23 +384,11 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       ps.tile_block = w.tile_block;
       ps.blocks = d_blocks;
       ps.weights = c->d_weights.p;
+      ps.taps = c->d_taps.p;
       ps.radius = R;
       rc = launch_recon(c, ps, wp, w.layer0, w.layer1, nullptr, c->d_acc.p);
       if (rc) return rc;
       launches++;
-    }
-    // ray counts of this wave (the counters are reused by the next one)
-    if (stats) {
-      const size_t used = (size_t)(bounces_run + 1) * CTR_STRIDE;
-      HJK_CUDA(c, cudaMemcpyAsync(c->h_counters.data(), c->d_counters.p, used * 4, cudaMemcpyDeviceToHost,
-                                  c->stream));
-      HJK_CUDA(c, cudaStreamSynchronize(c->stream));
-      resolve_timers(c, stats);
-      n_paths += c->h_counters[CTR_EXT];
-      for (uint32_t b = 0; b < bounces_run; b++) {
-        n_ext += c->h_counters[(size_t)b * CTR_STRIDE + CTR_EXT];
-        n_sh += c->h_counters[(size_t)b * CTR_STRIDE + CTR_SHADOW];
-      }
     }
     c->last_wave_passes = wp;
     c->have_features = true;
@@ -402,6 +398,9 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     HJK_CUDA(c, cudaEventSynchronize(c->ev1));
     resolve_timers(c, stats);
     if (stats) {
+      unsigned long long totals[3] = {0, 0, 0};
+      HJK_CUDA(c, cudaMemcpy(totals, c->d_totals.p, sizeof totals, cudaMemcpyDeviceToHost));
+      n_paths = totals[0], n_ext = totals[1], n_sh = totals[2];
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->ev0, c->ev1);
       stats->ms_total = ms;
@@ -459,11 +458,11 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, kTravThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true>, kTravThreads, 0);
   c->blocks_trav = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
   c->blocks_tile = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bin, kTileThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
   c->blocks_light = std::max(occ, 1);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail("kernel image (built for sm_100a)", e);
   *out_ctx = c;
@@ -711,12 +710,13 @@ int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int 
   HJK_CUDA(c, cudaMemcpyAsync(d_d.p, hd.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
   HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 4, c->stream));
   const float eps = 1e-4f;  // M_EPS, math.glsl:2
-  if (any_hit)
-    k_trace_batch<true><<<grid_for(c, c->blocks_trav), kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p,
-                                                                                    (uint32_t)n, d_cur.p, eps);
+  const int g = grid_for(c, c->blocks_trav);
+  const bool guard = c->scene.num_spheres != 0;
+  const uint32_t flavour = any_hit ? kAnyHitBit : 0u;
+  if (guard)
+    k_trace_batch<true><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour);
   else
-    k_trace_batch<false><<<grid_for(c, c->blocks_trav), kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p,
-                                                                                     (uint32_t)n, d_cur.p, eps);
+    k_trace_batch<false><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour);
   HJK_CUDA(c, cudaGetLastError());
   std::vector<f4> hh(n);
   HJK_CUDA(c, cudaMemcpyAsync(hh.data(), d_h.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -751,19 +751,21 @@ static int denoise_apply(HjkContext* c, const HjkParams* prm, uint32_t repeat, f
   const size_t nb = c->dn_blocks.size();
   HJK_CUDA(c, c->d_blocks.ensure(nb));
   HJK_CUDA(c, c->d_weights.ensure(nb * taps * taps));
+  HJK_CUDA(c, c->d_taps.ensure(nb * recon_tap_stride(R)));
   HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
   HJK_CUDA(c, cudaMemcpyAsync(c->d_blocks.p, c->dn_blocks.data(), nb * sizeof(HjkImageBlock), cudaMemcpyHostToDevice,
                               c->stream));
   HJK_CUDA(c, cudaMemcpyAsync(c->d_tile_block.p, plan.tile_block.data(), plan.tile_block.size() * 4,
                               cudaMemcpyHostToDevice, c->stream));
-  k_recon_weights<<<std::max<int>(1, (int)std::min<size_t>(1024, (nb * taps * taps + 255) / 256)), 256, 0, c->stream>>>(
-      c->d_blocks.p, (uint32_t)nb, R, prm->recon_stddev, c->d_weights.p);
+  k_recon_weights<<<std::max<int>(1, (int)std::min<size_t>(1024, (nb + 127) / 128)), 128, 0, c->stream>>>(
+      c->d_blocks.p, (uint32_t)nb, R, prm->recon_stddev, c->d_weights.p, c->d_taps.p);
   PassDev ps{};
   ps.width = plan.width, ps.height = plan.height, ps.tile_w = plan.tile_w, ps.tile_h = plan.tile_h;
   ps.tiles_x = plan.tiles_x, ps.tiles_y = plan.tiles_y;
   ps.tile_block = c->d_tile_block.p;
   ps.blocks = c->d_blocks.p;
   ps.weights = c->d_weights.p;
+  ps.taps = c->d_taps.p;
   ps.radius = R;
   HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   for (uint32_t i = 0; i < repeat; i++) {
@@ -879,6 +881,12 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "bvh_pad_rel_e9") {  // relative primitive-box pad in units of 1e-9 (next scene upload)
     if (value < 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "pad must be non-negative");
     c->bvh_pad_rel = (float)value * 1e-9f;
+  } else if (k == "fetch_threshold") {
+    if (value < 0 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->fetch_threshold = (uint32_t)value;
+  } else if (k == "postpone_lanes") {
+    if (value < 0 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->postpone_lanes = (uint32_t)value;
   } else if (k == "blocks_per_sm_traverse") {
     if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->blocks_trav = (int)value;

@@ -3,11 +3,13 @@
 // reconstruction dispatch (shader/reconstruction.glsl:22-66).
 //
 //   k_raygen    one thread per path slot: RNG seed, camera ray, layer initialisation
-//   k_traverse  persistent warps pull rays from a queue and walk the 8-wide BVH
-//               (closest hit = "extend", any hit = "shadow"), short stack in shared memory
-//   k_bin       ballot / prefix-sum compaction of the hits into one queue per material tag
-//   k_shade     material-sorted: emission, next-event estimation, BSDF sample, roulette;
-//               appends the next extension ray and the shadow ray by block-level compaction
+//   k_trace     persistent warps pull the extension rays of bounce b (closest hit = "extend") and
+//               the shadow rays of bounce b-1 (any hit) from one work range and walk the 8-wide
+//               BVH, short stack in shared memory
+//   k_shade     per tile of the queue: misses dropped, hits counting-sorted by material tag in
+//               shared memory (ballot / prefix sum), then emission, next-event estimation, BSDF
+//               sample, roulette; the next extension ray and the shadow ray are appended to their
+//               queues by block-level compaction
 //   k_recon     shared-memory tiled bilateral splat of one or more passes into the accumulator
 //
 // No host synchronisation inside a wave: every kernel reads its element count from device
@@ -50,7 +52,6 @@ struct WaveDev {
   f4* layer1;                    // (normal, depth)    render.glsl:173
   // queues
   uint32_t* ext_q[2];            // slot | wasDiscrete << 31
-  uint32_t* tag_q;               // [5][n_slots]
   f4* sh_o;                      // shadow rays, dense
   f4* sh_d;
   f4* sh_c;                      // contribution.rgb, slot bits
@@ -60,6 +61,8 @@ struct WaveDev {
   int32_t recon_radius;
   float eps;
   uint32_t has_extinction;
+  uint32_t fetch_threshold;      // refill a warp when fewer lanes than this are busy
+  uint32_t postpone_lanes;       // postpone primitive tests that fewer lanes than this would run
 };
 
 constexpr int kTravThreads = 128;
@@ -67,6 +70,7 @@ constexpr int kSmStack = 8;       // stack entries kept in shared memory per thr
 constexpr int kLocalStack = 24;   // overflow entries in local memory
 constexpr int kMaxStack = kSmStack + kLocalStack;
 constexpr int kFetchThreshold = 20;  // refill a warp when fewer lanes than this are busy
+constexpr int kPostponeLanes = 8;    // postpone primitive tests that fewer lanes than this would run
 constexpr int kTileThreads = 256;
 
 // ---------------------------------------------------------------- block-level compaction
@@ -164,32 +168,39 @@ struct DevStack {
   __device__ __forceinline__ bool empty() const { return n == 0; }
 };
 
-// Source of rays / sink of results for the two traversal flavours.
-struct ExtendIO {  // closest hit over the extension queue of `bounce`
+// Source of rays / sink of results of a traversal launch.  A ray's flavour rides in the top bit of
+// TravState::slot: 1 = any hit (shadow ray), 0 = closest hit (extension ray).
+constexpr uint32_t kAnyHitBit = 0x80000000u;
+
+// One bounce step of the wave: the shadow rays emitted by bounce-1 and the extension rays of
+// `bounce` are drawn from ONE work range [0, n_shadow + n_ext) by the same persistent warps, so a
+// launch has one tail instead of two and shadow rays fill the lanes extension rays leave idle.
+struct WaveIO {
   const WaveDev& w;
-  const uint32_t* queue;
+  const uint32_t* queue;  // extension queue of this bounce
+  uint32_t n_shadow;
+  template <bool GUARD>
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
-    const uint32_t slot = queue[i] & 0x7FFFFFFFu;
-    s.slot = slot;
-    trav_init(s, w.scene, w.ray_o[slot], w.ray_d[slot]);
+    if (i < n_shadow) {  // dense shadow queue
+      s.slot = i | kAnyHitBit;
+      trav_init<GUARD>(s, w.scene, w.sh_o[i], w.sh_d[i]);
+    } else {
+      const uint32_t slot = queue[i - n_shadow] & 0x7FFFFFFFu;
+      s.slot = slot;
+      trav_init<GUARD>(s, w.scene, w.ray_o[slot], w.ray_d[slot]);
+    }
   }
   __device__ __forceinline__ void store(const TravState& s) const {
-    w.hit[s.slot] = F4(__int_as_float(s.hit_id), s.hit_t, s.hit_u, s.hit_v);
-  }
-};
-struct ShadowIO {  // any hit over the dense shadow queue; visible -> add the contribution
-  const WaveDev& w;
-  __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
-    s.slot = i;
-    trav_init(s, w.scene, w.sh_o[i], w.sh_d[i]);
-  }
-  __device__ __forceinline__ void store(const TravState& s) const {
-    if (s.hit_id >= 0) return;  // occluded (render.glsl:122)
-    const f4 c = w.sh_c[s.slot];
-    const uint32_t slot = __float_as_uint(c.w);
-    f4 r = w.layer0[slot];      // total += throughput * evalBSDF * importance (render.glsl:123)
-    r.x = x::add(r.x, c.x), r.y = x::add(r.y, c.y), r.z = x::add(r.z, c.z);
-    w.layer0[slot] = r;
+    if (s.slot & kAnyHitBit) {
+      if (s.hit_id >= 0) return;  // occluded (render.glsl:122)
+      const f4 c = w.sh_c[s.slot & ~kAnyHitBit];
+      const uint32_t slot = __float_as_uint(c.w);
+      f4 r = w.layer0[slot];      // total += throughput * evalBSDF * importance (render.glsl:123)
+      r.x = x::add(r.x, c.x), r.y = x::add(r.y, c.y), r.z = x::add(r.z, c.z);
+      w.layer0[slot] = r;
+    } else {
+      w.hit[s.slot] = F4(__int_as_float(s.hit_id), s.hit_t, s.hit_u, s.hit_v);
+    }
   }
 };
 // Standalone ray batch (hjk_trace_first_hit): rays and results are indexed by ray number.
@@ -198,20 +209,30 @@ struct BatchIO {
   const f4* ray_o;
   const f4* ray_d;
   f4* hit;
+  uint32_t flavour;  // kAnyHitBit or 0 for the whole batch
+  template <bool GUARD>
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
-    s.slot = i;
-    trav_init(s, sc, ray_o[i], ray_d[i]);
+    s.slot = i | flavour;
+    trav_init<GUARD>(s, sc, ray_o[i], ray_d[i]);
   }
   __device__ __forceinline__ void store(const TravState& s) const {
-    hit[s.slot] = F4(__int_as_float(s.hit_id), s.hit_t, s.hit_u, s.hit_v);
+    hit[s.slot & ~kAnyHitBit] = F4(__int_as_float(s.hit_id), s.hit_t, s.hit_u, s.hit_v);
   }
 };
 
-// Persistent warps: each warp keeps its 32 lanes supplied with rays from the queue; a lane
-// whose ray finishes is refilled as soon as fewer than kFetchThreshold lanes are busy.
-template <bool ANY_HIT, class IO>
+struct WarpPolicy {
+  bool can_refill;
+  int fetch_threshold, postpone_lanes;
+  __device__ __forceinline__ bool yield() const { return can_refill && __popc(__activemask()) < fetch_threshold; }
+  __device__ __forceinline__ bool postpone() const { return __popc(__activemask()) < postpone_lanes; }
+};
+
+// Persistent warps: each warp keeps its 32 lanes supplied with rays from the work range; a lane
+// whose ray finishes is refilled as soon as fewer than `fetch_threshold` lanes are busy.
+template <bool GUARD, class IO>
 __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io, uint32_t n,
-                                               uint32_t* cursor, float eps) {
+                                               uint32_t* cursor, float eps, int fetch_threshold,
+                                               int postpone_lanes) {
   __shared__ uint2 sm_stack[kSmStack * kTravThreads];
   const uint32_t lane = threadIdx.x & 31u;
   DevStack st;
@@ -229,7 +250,7 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
         if (!active) {
           const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
           if (i < n) {
-            io.load(i, s);
+            io.template load<GUARD>(i, s);
             st.n = 0;
             active = true;
           }
@@ -239,9 +260,8 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
     }
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
     if (active) {
-      const bool done = trav_run<ANY_HIT>(sc, s, st, eps, [&]() {
-        return !exhausted && __popc(__activemask()) < kFetchThreshold;
-      });
+      const WarpPolicy policy{!exhausted, fetch_threshold, postpone_lanes};
+      const bool done = trav_run<GUARD>(sc, s, st, eps, policy);
       if (done) {
         io.store(s);
         active = false;
@@ -251,34 +271,48 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
   }
 }
 
-__global__ void __launch_bounds__(kTravThreads) k_extend(WaveDev w, uint32_t bounce) {
+// GUARD: the scene contains spheres (sphere guard of traverse.cuh compiled in).
+// bounce in [0, max_bounces]: extension rays of `bounce` (none at max_bounces) + shadow rays of bounce-1.
+template <bool GUARD>
+__global__ void __launch_bounds__(kTravThreads) k_trace(WaveDev w, uint32_t bounce, uint32_t last) {
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
-  const ExtendIO io{w, w.ext_q[bounce & 1u]};
-  traverse_queue<false>(w.scene, io, ctr[CTR_EXT], ctr + CTR_EXT_CURSOR, w.eps);
+  const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
+  const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
+  const WaveIO io{w, w.ext_q[bounce & 1u], n_shadow};
+  traverse_queue<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
+                        (int)w.postpone_lanes);
 }
-__global__ void __launch_bounds__(kTravThreads) k_shadow(WaveDev w, uint32_t bounce) {
-  uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
-  const ShadowIO io{w};
-  traverse_queue<true>(w.scene, io, ctr[CTR_SHADOW], ctr + CTR_SH_CURSOR, w.eps);
-}
-// counters: [0] = cursor
-template <bool ANY_HIT>
+template <bool GUARD>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
-                                                              f4* hit, uint32_t n, uint32_t* cursor, float eps) {
-  const BatchIO io{sc, ray_o, ray_d, hit};
-  traverse_queue<ANY_HIT>(sc, io, n, cursor, eps);
+                                                              f4* hit, uint32_t n, uint32_t* cursor, float eps,
+                                                              uint32_t flavour) {
+  const BatchIO io{sc, ray_o, ray_d, hit, flavour};
+  traverse_queue<GUARD>(sc, io, n, cursor, eps, kFetchThreshold, kPostponeLanes);
 }
 
-// ---------------------------------------------------------------- material binning
-// Splits the hits of one bounce into one queue per material tag (material-sorted shading);
-// misses leave the pipeline here (render.glsl:94-96).
-__global__ void __launch_bounds__(kTileThreads) k_bin(WaveDev w, uint32_t bounce) {
-  __shared__ BlockAppend<5> sm;
+// ---------------------------------------------------------------- sort + shade
+// Material-sorted shading of one bounce.  Each CTA takes a tile of the bounce's extension queue,
+// drops the misses (render.glsl:94-96), counting-sorts the hits of the tile by material tag in
+// shared memory (warp ballots + prefix sums) so that its warps shade one material each, then runs
+// one bounce-loop iteration per hit and appends the next extension ray and the shadow ray to
+// their queues by block-level compaction.
+struct TileSort {
+  uint32_t warp_count[5][kTileThreads / 32];
+  uint32_t tag_base[6];
+  uint32_t entry[kTileThreads];
+};
+
+__global__ void __launch_bounds__(kTileThreads, 4) k_shade(WaveDev w, uint32_t bounce) {
+  __shared__ BlockAppend<2> sm;
+  __shared__ TileSort ts;
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n = ctr[CTR_EXT];
   const uint32_t* q = w.ext_q[bounce & 1u];
+  uint32_t* next_q = w.ext_q[(bounce + 1u) & 1u];
   const uint32_t n_tiles = (n + kTileThreads - 1) / kTileThreads;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- tile-local material sort
     const uint32_t i = tile * kTileThreads + threadIdx.x;
     uint32_t entry = 0, tag = 0xFFFFFFFFu;
     if (i < n) {
@@ -286,36 +320,37 @@ __global__ void __launch_bounds__(kTileThreads) k_bin(WaveDev w, uint32_t bounce
       const int id = __float_as_int(w.hit[entry & 0x7FFFFFFFu].x);
       if (id >= 0) tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
     }
-    const bool flag[5] = {tag == 0u, tag == 1u, tag == 2u, tag == 3u, tag == 4u};
-    uint32_t* const c[5] = {ctr + CTR_TAG0, ctr + CTR_TAG0 + 1, ctr + CTR_TAG0 + 2, ctr + CTR_TAG0 + 3,
-                            ctr + CTR_TAG0 + 4};
-    uint32_t pos[5];
-    block_append<5>(sm, flag, c, pos);
-    if (tag < 5u) w.tag_q[(size_t)tag * w.n_slots + pos[tag]] = entry;
-  }
-}
-
-// ---------------------------------------------------------------- shade
-__global__ void __launch_bounds__(kTileThreads) k_shade(WaveDev w, uint32_t bounce) {
-  __shared__ BlockAppend<2> sm;
-  uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
-  uint32_t first[6];
-  first[0] = 0;
+    uint32_t prefix = 0;
 #pragma unroll
-  for (int t = 0; t < 5; t++) first[t + 1] = first[t] + ctr[CTR_TAG0 + t];
-  const uint32_t n = first[5];
-  const uint32_t n_tiles = (n + kTileThreads - 1) / kTileThreads;
-  uint32_t* next_q = w.ext_q[(bounce + 1u) & 1u];
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t i = tile * kTileThreads + threadIdx.x;
+    for (uint32_t t = 0; t < 5; t++) {
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, tag == t);
+      if (tag == t) prefix = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) ts.warp_count[t][warp] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (uint32_t t = 0; t < 5; t++) {
+        ts.tag_base[t] = total;
+        for (uint32_t wi = 0; wi < kTileThreads / 32; wi++) {
+          const uint32_t c = ts.warp_count[t][wi];
+          ts.warp_count[t][wi] = total;
+          total += c;
+        }
+      }
+      ts.tag_base[5] = total;
+    }
+    __syncthreads();
+    if (tag < 5u) ts.entry[ts.warp_count[tag][warp] + prefix] = entry;
+    __syncthreads();
+    const uint32_t n_hits = ts.tag_base[5];
+
+    // ---- one bounce-loop iteration per hit
     bool want_next = false, want_shadow = false;
     VertexOut out;
     uint32_t slot = 0;
-    if (i < n) {
-      uint32_t tag = 0;
-#pragma unroll
-      for (int t = 1; t < 5; t++) tag += (i >= first[t]) ? 1u : 0u;
-      const uint32_t entry = w.tag_q[(size_t)tag * w.n_slots + (i - first[tag])];
+    if (threadIdx.x < n_hits) {
+      entry = ts.entry[threadIdx.x];
       slot = entry & 0x7FFFFFFFu;
       VertexIn in;
       in.ray_o = w.ray_o[slot];
@@ -347,7 +382,7 @@ __global__ void __launch_bounds__(kTileThreads) k_shade(WaveDev w, uint32_t boun
     const bool flag[2] = {want_next, want_shadow};
     uint32_t* const c[2] = {ctr + CTR_STRIDE + CTR_EXT, ctr + CTR_SHADOW};
     uint32_t pos[2];
-    block_append<2>(sm, flag, c, pos);
+    block_append<2>(sm, flag, c, pos);  // ends with a barrier: ts may be overwritten by the next tile
     if (want_next) next_q[pos[0]] = slot | (out.was_discrete ? 0x80000000u : 0u);
     if (want_shadow) {
       w.sh_o[pos[1]] = out.sh_o;
@@ -359,16 +394,11 @@ __global__ void __launch_bounds__(kTileThreads) k_shade(WaveDev w, uint32_t boun
 
 // ---------------------------------------------------------------- reconstruction
 __global__ void k_recon_weights(const HjkImageBlock* blocks, uint32_t n_blocks, int radius, float stddev,
-                                float* weights) {
-  const int taps = 2 * radius + 1;
-  const uint32_t total = n_blocks * (uint32_t)(taps * taps);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t b = i / (uint32_t)(taps * taps);
-    const int k = (int)(i - b * (uint32_t)(taps * taps));
-    const int dx = k / taps - radius, dy = k % taps - radius;
-    weights[i] = recon_spatial_weight(dx, dy, radius, stddev, blocks[b].sample_offset[0],
-                                      blocks[b].sample_offset[1]);
-  }
+                                float* weights, uint32_t* taps) {
+  const int t2 = (2 * radius + 1) * (2 * radius + 1);
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += gridDim.x * blockDim.x)
+    recon_fill_block_tables(blocks[b], radius, stddev, weights + (size_t)b * t2,
+                            taps + (size_t)b * recon_tap_stride(radius));
 }
 
 constexpr int kReconTileX = 32, kReconTileY = 16;
@@ -403,12 +433,16 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY)
   f4* s1 = s0 + pitch * rows;
   f4* s2 = s1 + pitch * rows;
   const int x0 = (int)blockIdx.x * kReconTileX - R, y0 = (int)blockIdx.y * kReconTileY - R;
-  const uint32_t gx = blockIdx.x * kReconTileX + threadIdx.x, gy = blockIdx.y * kReconTileY + threadIdx.y;
+  // a warp covers 4 x 8 texels, not 32 x 1: texels within R of a block edge run a second (or
+  // fourth) block's tap list, and narrow warps keep those few texels from stalling 28 others
+  const int tid = threadIdx.y * kReconTileX + threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t gx = blockIdx.x * kReconTileX + 4u * (warp & 7) + (lane & 3);
+  const uint32_t gy = blockIdx.y * kReconTileY + 8u * (warp >> 3) + (lane >> 2);
   const bool in_image = gx < ps.width && gy < ps.height;
   const size_t n_pixels = (size_t)ps.width * ps.height;
   f4 acc = F4(0.f, 0.f, 0.f, 0.f);
   if (in_image) acc = accumulator[(size_t)gy * ps.width + gx];
-  const int tid = threadIdx.y * kReconTileX + threadIdx.x;
   for (uint32_t p = 0; p < n_passes; p++) {
     const f4* l0 = layer0 + p * n_pixels;
     const f4* l1 = layer1 + p * n_pixels;
@@ -443,6 +477,24 @@ __global__ void k_normalise(const f4* acc, f4* out, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const f4 a = acc[i];
     out[i] = F4(x::div(a.x, a.w), x::div(a.y, a.w), x::div(a.z, a.w), a.w);
+  }
+}
+
+// paths / extension rays / shadow rays of one wave, added to the call's totals
+__global__ void k_wave_totals(const uint32_t* counters, uint32_t n_rows, unsigned long long* totals) {
+  unsigned long long ext = 0, sh = 0;
+  for (uint32_t r = threadIdx.x; r < n_rows; r += 32) {
+    ext += counters[(size_t)r * CTR_STRIDE + CTR_EXT];
+    sh += counters[(size_t)r * CTR_STRIDE + CTR_SHADOW];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ext += __shfl_down_sync(0xFFFFFFFFu, ext, o);
+    sh += __shfl_down_sync(0xFFFFFFFFu, sh, o);
+  }
+  if (threadIdx.x == 0) {
+    totals[0] += counters[CTR_EXT];
+    totals[1] += ext;
+    totals[2] += sh;
   }
 }
 

@@ -51,7 +51,7 @@ struct TravState {
   uint32_t tg_x, tg_y;   // primitive group: first record index, pending hit bits
   int32_t hit_id;        // global shape id of the current winner, -1 = none
   float hit_t, hit_u, hit_v;
-  uint32_t slot;         // caller payload (path slot / ray index)
+  uint32_t slot;         // caller payload (path slot / ray index); top bit = any-hit ray
   // sphere guard (see trav_init): per-axis box inflation in t units, box-test interval
   float infl_x, infl_y, infl_z;
   float box_tmin, box_tmax_scale;
@@ -73,6 +73,8 @@ HJK_HD float safe_rcp(float d) {
 // interval is [0, tMax * max(1, 1/s^2)].  For |s^2 - 1| of a few ulps this degenerates to a
 // pad of ~1e-7 L^2 / r; for scenes without spheres it is switched off (triangle and quad tests
 // are homogeneous in d, hence geometric for any s).
+// GUARD = the scene contains spheres (a per-scene constant: kernels are instantiated for both).
+template <bool GUARD>
 HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const f4& d_tmax) {
   s.ox = o_tmin.x, s.oy = o_tmin.y, s.oz = o_tmin.z, s.tmin = o_tmin.w;
   s.dx = d_tmax.x, s.dy = d_tmax.y, s.dz = d_tmax.z, s.tmax = d_tmax.w;
@@ -80,7 +82,7 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
   s.infl_x = s.infl_y = s.infl_z = 0.f;
   s.box_tmin = s.tmin;
   s.box_tmax_scale = 1.0f;
-  if (sc.num_spheres) {
+  if (GUARD) {
     const float s2 = s.dx * s.dx + s.dy * s.dy + s.dz * s.dz;
     const float lx = s.ox - sc.sph_centre[0], ly = s.oy - sc.sph_centre[1], lz = s.oz - sc.sph_centre[2];
     const float L = sqrtf(lx * lx + ly * ly + lz * lz) + sc.sph_centre[3];
@@ -111,6 +113,7 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
 
 // 8 child boxes of one node against the ray interval; returns the 32-bit hit mask
 // (bits 31..24: inner children in near-to-far priority order, bits 23..0: primitives).
+template <bool GUARD>
 HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, const f4& q2,
                                const f4& q3, const f4& q4) {
   const uint32_t e_imask = x::as_uint(q0.w);
@@ -121,9 +124,12 @@ HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, c
   const float orgy = (q0.y - s.oy) * s.idy;
   const float orgz = (q0.z - s.oz) * s.idz;
   // near planes move towards the origin, far planes away from it, by the sphere-guard inflation
-  const float o0x = orgx - s.infl_x, o0y = orgy - s.infl_y, o0z = orgz - s.infl_z;
-  const float o1x = orgx + s.infl_x, o1y = orgy + s.infl_y, o1z = orgz + s.infl_z;
-  const float box_tmax = s.tmax * s.box_tmax_scale;
+  const float o0x = GUARD ? orgx - s.infl_x : orgx, o0y = GUARD ? orgy - s.infl_y : orgy,
+              o0z = GUARD ? orgz - s.infl_z : orgz;
+  const float o1x = GUARD ? orgx + s.infl_x : orgx, o1y = GUARD ? orgy + s.infl_y : orgy,
+              o1z = GUARD ? orgz + s.infl_z : orgz;
+  const float box_tmin = GUARD ? s.box_tmin : s.tmin;
+  const float box_tmax = GUARD ? s.tmax * s.box_tmax_scale : s.tmax;
   const bool nx = s.idx < 0.f, ny = s.idy < 0.f, nz = s.idz < 0.f;
   uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
@@ -151,7 +157,7 @@ HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, c
       const float t1x = fmaf(byte_to_float(farx, j), adjx, o1x);
       const float t1y = fmaf(byte_to_float(fary, j), adjy, o1y);
       const float t1z = fmaf(byte_to_float(farz, j), adjz, o1z);
-      const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.box_tmin));
+      const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, box_tmin));
       const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, box_tmax));
       if (cmin <= cmax) {
         const uint32_t bits = (child_bits4 >> (8 * j)) & 0xFFu;
@@ -218,11 +224,21 @@ HJK_HD bool intersect_prim(const SceneDev& sc, const TravState& s, const f4& r0,
   return false;
 }
 
-// Runs the traversal until the ray is finished (returns true) or `yield()` asks to stop
-// (returns false; call again with the same state to resume).
+// Scheduling policy of the host-side harness and of single-ray callers: never yield, never postpone.
+struct TravNoPolicy {
+  HJK_HD bool yield() const { return false; }
+  HJK_HD bool postpone() const { return false; }
+};
+
+// Runs the traversal until the ray is finished (returns true) or `policy.yield()` asks to stop
+// (returns false; call again with the same state to resume).  `policy.postpone()` is asked inside
+// the primitive loop: when it says yes and the lane still has inner-node work, the pending
+// primitives go to the stack and are tested later, when more lanes of the warp have primitive work
+// (only the visiting order changes, never what is accepted).
 //   Stack: push(uint32_t, uint32_t), pop(uint32_t&, uint32_t&), empty().
-template <bool ANY_HIT, class Stack, class Yield>
-HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, Yield&& yield) {
+// Any-hit rays (top bit of s.slot set) return at the first accepted primitive.
+template <bool GUARD, class Stack, class Policy>
+HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, const Policy& policy) {
   for (;;) {
     if (s.ng_y > 0x00FFFFFFu) {
       const uint32_t hits_imask = s.ng_y;
@@ -233,7 +249,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       const uint32_t rel = (uint32_t)pop_count(hits_imask & ~(0xFFFFFFFFu << slot));
       const f4* np = sc.nodes + (size_t)(s.ng_x + rel) * 5;
       const f4 q0 = ld16(np), q1 = ld16(np + 1), q2 = ld16(np + 2), q3 = ld16(np + 3), q4 = ld16(np + 4);
-      const uint32_t hitmask = intersect_node(s, q0, q1, q2, q3, q4);
+      const uint32_t hitmask = intersect_node<GUARD>(s, q0, q1, q2, q3, q4);
       s.ng_x = x::as_uint(q1.x);
       s.ng_y = (hitmask & 0xFF000000u) | (x::as_uint(q0.w) >> 24);
       s.tg_x = x::as_uint(q1.y);
@@ -243,6 +259,10 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       s.ng_x = s.ng_y = 0;
     }
     while (s.tg_y) {
+      if (s.ng_y > 0x00FFFFFFu && policy.postpone()) {
+        stack.push(s.tg_x, s.tg_y);
+        break;
+      }
       const int i = hi_bit(s.tg_y);
       s.tg_y &= ~(1u << i);
       const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * 3;
@@ -251,7 +271,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       if (intersect_prim(sc, s, r0, r1, r2, t, u, v)) {
         s.hit_id = (int32_t)x::as_uint(r0.w);
         s.hit_t = t, s.hit_u = u, s.hit_v = v;
-        if (ANY_HIT) return true;
+        if (s.slot >> 31) return true;
         s.tmax = x::sub(t, eps);  // scene.glsl:116
       }
     }
@@ -259,7 +279,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       if (stack.empty()) return true;
       stack.pop(s.ng_x, s.ng_y);
     }
-    if (yield()) return false;
+    if (policy.yield()) return false;
   }
 }
 

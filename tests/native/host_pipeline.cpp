@@ -34,6 +34,26 @@ struct HostStack {
   bool empty() const { return n == 0; }
 };
 
+// Scheduling stress: postpones and yields on a fixed pseudo-random pattern, so the resumable state
+// machine and the primitive postponing of trav_run are exercised on the CPU (bit 1 of ht_trace's mode).
+struct ChaosPolicy {
+  mutable uint32_t state;
+  bool next() const {
+    state = state * 1664525u + 1013904223u;
+    return (state >> 28) < 6u;
+  }
+  bool yield() const { return next(); }
+  bool postpone() const { return next(); }
+};
+
+// the kernels are instantiated per scene for GUARD = "has spheres"; mirror that choice here
+template <bool ANY_HIT, class Policy>
+bool run_ray(const SceneDev& sc, TravState& s, struct HostStack& st, float eps, const Policy& p);
+template <class F4>
+void init_ray(const SceneDev& sc, TravState& s, const F4& o, const F4& d) {
+  if (sc.num_spheres) trav_init<true>(s, sc, o, d); else trav_init<false>(s, sc, o, d);
+}
+
 struct Harness {
   WideBvh bvh;
   SceneDev sc{};
@@ -61,6 +81,12 @@ struct FrameLayers {
   f4 feature(uint32_t gx, uint32_t gy) const { return at(l1, gx, gy); }
   f4 albedo(uint32_t gx, uint32_t gy) const { return at(l2, gx, gy); }
 };
+
+template <bool ANY_HIT, class Policy>
+bool run_ray(const SceneDev& sc, TravState& s, HostStack& st, float eps, const Policy& p) {
+  s.slot = ANY_HIT ? 0x80000000u : 0u;
+  return sc.num_spheres ? trav_run<true>(sc, s, st, eps, p) : trav_run<false>(sc, s, st, eps, p);
+}
 
 }  // namespace
 
@@ -119,15 +145,26 @@ void ht_trace(void* p, const HjkRay* rays, uint64_t n, int any_hit, float eps, i
   Harness* h = (Harness*)p;
   for (uint64_t i = 0; i < n; i++) {
     TravState s;
-    trav_init(s, h->sc, F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min),
+    init_ray(h->sc, s, F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min),
               F4(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2], rays[i].t_max));
     HostStack st;
-    auto never = []() { return false; };
-    if (any_hit) {
-      trav_run<true>(h->sc, s, st, eps, never);
+    const TravNoPolicy never;
+    const ChaosPolicy chaos{(uint32_t)i * 2654435761u + 12345u};
+    if (any_hit & 1) {
+      if (any_hit & 2) {
+        while (!run_ray<true>(h->sc, s, st, eps, chaos)) {
+        }
+      } else {
+        run_ray<true>(h->sc, s, st, eps, never);
+      }
       shape_id[i] = s.hit_id >= 0 ? 1 : 0;
     } else {
-      trav_run<false>(h->sc, s, st, eps, never);
+      if (any_hit & 2) {
+        while (!run_ray<false>(h->sc, s, st, eps, chaos)) {
+        }
+      } else {
+        run_ray<false>(h->sc, s, st, eps, never);
+      }
       shape_id[i] = s.hit_id;
     }
     if (st.max_n > h->max_stack) h->max_stack = st.max_n;
@@ -155,11 +192,10 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
   float* l2 = l1 + npx * 4;
   const int R = (int)prm->recon_radius, taps = 2 * R + 1;
   std::vector<float> weights((size_t)n_blocks * taps * taps);
+  std::vector<uint32_t> tap_lists((size_t)n_blocks * recon_tap_stride(R));
   for (uint64_t b = 0; b < n_blocks; b++)
-    for (int dx = -R; dx <= R; dx++)
-      for (int dy = -R; dy <= R; dy++)
-        weights[b * taps * taps + (dx + R) * taps + (dy + R)] = recon_spatial_weight(
-            dx, dy, R, prm->recon_stddev, blocks[b].sample_offset[0], blocks[b].sample_offset[1]);
+    recon_fill_block_tables(blocks[b], R, prm->recon_stddev, weights.data() + b * taps * taps,
+                            tap_lists.data() + b * recon_tap_stride(R));
   uint64_t n_paths = 0, n_ext = 0, n_sh = 0;
   const size_t tiles = (size_t)plan.tiles_x * plan.tiles_y;
   for (size_t pi = 0; pi < plan.passes.size(); pi++) {
@@ -189,11 +225,11 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
           in.bounce = bounce;
           // extend
           TravState s;
-          trav_init(s, h->sc, in.ray_o, in.ray_d);
+          init_ray(h->sc, s, in.ray_o, in.ray_d);
           HostStack st;
-          auto never = []() { return false; };
+          const TravNoPolicy never;
           n_ext++;
-          trav_run<false>(h->sc, s, st, prm->eps, never);
+          run_ray<false>(h->sc, s, st, prm->eps, never);
           if (s.hit_id < 0) break;
           in.hit_id = s.hit_id, in.hit_t = s.hit_t, in.hit_u = s.hit_u, in.hit_v = s.hit_v;
           // shade
@@ -207,9 +243,9 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
           if (o.has_shadow) {
             n_sh++;
             TravState ss;
-            trav_init(ss, h->sc, o.sh_o, o.sh_d);
+            init_ray(h->sc, ss, o.sh_o, o.sh_d);
             HostStack st2;
-            trav_run<true>(h->sc, ss, st2, prm->eps, never);
+            run_ray<true>(h->sc, ss, st2, prm->eps, never);
             if (ss.hit_id < 0) {
               r[0] = x::add(r[0], o.contribution.x), r[1] = x::add(r[1], o.contribution.y),
               r[2] = x::add(r[2], o.contribution.z);
@@ -228,6 +264,8 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
       ps.tile_block = tile_block;
       ps.blocks = blocks;
       ps.weights = weights.data();
+    ps.taps = tap_lists.data();
+      ps.taps = tap_lists.data();
       ps.radius = R;
       FrameLayers L{l0, l1, l2, W};
       for (uint32_t gy = 0; gy < H; gy++)
@@ -257,7 +295,7 @@ int ht_trace_path(void* p, const HjkImageBlock* blk, uint32_t lx, uint32_t ly, c
   in.extinction = V3(0.f);
   in.was_discrete = true;
   int n = 0;
-  auto never = []() { return false; };
+  const TravNoPolicy never;
   for (uint32_t bounce = 0; bounce < prm->max_bounces && n < capacity; bounce++) {
     in.bounce = bounce;
     if (rays_out) {
@@ -265,9 +303,9 @@ int ht_trace_path(void* p, const HjkImageBlock* blk, uint32_t lx, uint32_t ly, c
       memcpy(rays_out + 8 * n + 4, &in.ray_d, 16);
     }
     TravState s;
-    trav_init(s, h->sc, in.ray_o, in.ray_d);
+    init_ray(h->sc, s, in.ray_o, in.ray_d);
     HostStack st;
-    trav_run<false>(h->sc, s, st, prm->eps, never);
+    run_ray<false>(h->sc, s, st, prm->eps, never);
     int32_t* o = out + 4 * n++;
     o[0] = s.hit_id;
     memcpy(&o[1], &s.hit_t, 4);
@@ -279,9 +317,9 @@ int ht_trace_path(void* p, const HjkImageBlock* blk, uint32_t lx, uint32_t ly, c
     o[2] = (int32_t)vo.rng;
     if (vo.has_shadow) {
       TravState ss;
-      trav_init(ss, h->sc, vo.sh_o, vo.sh_d);
+      init_ray(h->sc, ss, vo.sh_o, vo.sh_d);
       HostStack st2;
-      trav_run<true>(h->sc, ss, st2, prm->eps, never);
+      run_ray<true>(h->sc, ss, st2, prm->eps, never);
       o[3] = ss.hit_id < 0 ? 2 : 1;
     }
     if (!vo.continues) break;
@@ -300,11 +338,10 @@ int ht_denoise(const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* 
   if (!plan_passes(blocks, n_blocks, plan, err)) return -1;
   const int R = (int)prm->recon_radius, taps = 2 * R + 1;
   std::vector<float> weights((size_t)n_blocks * taps * taps);
+  std::vector<uint32_t> tap_lists((size_t)n_blocks * recon_tap_stride(R));
   for (uint64_t b = 0; b < n_blocks; b++)
-    for (int dx = -R; dx <= R; dx++)
-      for (int dy = -R; dy <= R; dy++)
-        weights[b * taps * taps + (dx + R) * taps + (dy + R)] = recon_spatial_weight(
-            dx, dy, R, prm->recon_stddev, blocks[b].sample_offset[0], blocks[b].sample_offset[1]);
+    recon_fill_block_tables(blocks[b], R, prm->recon_stddev, weights.data() + b * taps * taps,
+                            tap_lists.data() + b * recon_tap_stride(R));
   const size_t tiles = (size_t)plan.tiles_x * plan.tiles_y;
   for (size_t pi = 0; pi < plan.passes.size(); pi++) {
     PassDev ps;
@@ -313,6 +350,7 @@ int ht_denoise(const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* 
     ps.tile_block = plan.tile_block.data() + pi * tiles;
     ps.blocks = blocks;
     ps.weights = weights.data();
+    ps.taps = tap_lists.data();
     ps.radius = R;
     FrameLayers L{radiance, normal_depth, albedo, plan.width};
     for (uint32_t gy = 0; gy < plan.height; gy++)
