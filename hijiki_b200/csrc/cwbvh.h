@@ -33,12 +33,20 @@ static_assert(sizeof(WideNode) == 80, "WideNode must be five 16-byte words");
 //             shapes/triangle.glsl:19-20 computes them per ray)
 //   sphere  : r0 = (centre.xyz, id) r1 = (radius, 0,0,0) r2 = 0
 //   quad    : r0 = (origin.xyz, id) r1 = (edge1, 0)      r2 = (edge2, 0)
+// HJK_PRIM_STRIDE = 4 adds r3 = (cross(r1, r2), 0): the fp32 cross product the reference evaluates
+// per ray (shapes/triangle.glsl:22), precomputed with the same separately rounded operations.
+#ifndef HJK_PRIM_STRIDE
+#define HJK_PRIM_STRIDE 3
+#endif
 struct WidePrim {
   float r0[4];
   float r1[4];
   float r2[4];
+#if HJK_PRIM_STRIDE == 4
+  float r3[4];
+#endif
 };
-static_assert(sizeof(WidePrim) == 48, "WidePrim must be three 16-byte words");
+static_assert(sizeof(WidePrim) == 16 * HJK_PRIM_STRIDE, "WidePrim must be whole 16-byte words");
 
 enum : uint32_t { kWideMaxLeafPrims = 3, kWideMaxNodePrims = 24 };
 

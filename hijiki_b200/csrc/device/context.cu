@@ -96,7 +96,7 @@ struct HjkContext {
   int blocks_light = 0;                  // ... of the light tile kernels (raygen, bin)
   std::string error;
   bool profiling = false;
-  uint64_t wave_paths = 16u << 20;  // target camera paths per wave (2.7 GB of path state; tails amortise)
+  uint64_t wave_paths = 32u << 20;  // target camera paths per wave (4.9 GB of path state; tails amortise)
   float bvh_pad_rel = kDefaultBvhPadRel;
   uint32_t fetch_threshold = kFetchThreshold, postpone_lanes = kPostponeLanes;
 

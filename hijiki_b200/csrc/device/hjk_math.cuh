@@ -207,6 +207,25 @@ HJK_HD float exp_det(float a) {
   return y;
 }
 
+// exp_det(-e) for e >= 0 (or NaN), bit for bit, with the work the sign makes unnecessary removed:
+// no overflow test, and n = round(-e log2 e) lies in [-126, 0], so 2^n is built in one piece
+// (y * 2^(n/2) * 2^(n - n/2) and y * 2^n round identically: the first product is exact).
+HJK_HD float exp_det_neg(float e) {
+  if (!(e <= 87.3365402f)) return e != e ? -e : 0.0f;
+  const float a = -e;
+  float n = x::floor(x::add(x::mul(a, 1.44269504088896341f), 0.5f));
+  float r = x::sub(a, x::mul(n, 0.693359375f));
+  r = x::sub(r, x::mul(n, -2.12194440e-4f));
+  float z = x::mul(r, r);
+  float p = x::add(x::mul(1.9875691500e-4f, r), 1.3981999507e-3f);
+  p = x::add(x::mul(p, r), 8.3334519073e-3f);
+  p = x::add(x::mul(p, r), 4.1665795894e-2f);
+  p = x::add(x::mul(p, r), 1.6666665459e-1f);
+  p = x::add(x::mul(p, r), 5.0000001201e-1f);
+  float y = x::add(x::add(x::mul(p, z), r), 1.0f);
+  return x::mul(y, x::as_float((uint32_t)((int)n + 127) << 23));
+}
+
 // atan on the whole line (Cephes atanf), then atan2 by quadrant.
 HJK_HD float atan_det(float a) {
   if (x::is_nan(a)) return a;

@@ -66,8 +66,11 @@ struct WaveDev {
 };
 
 constexpr int kTravThreads = 128;
-constexpr int kSmStack = 8;       // stack entries kept in shared memory per thread
-constexpr int kLocalStack = 24;   // overflow entries in local memory
+#ifndef HJK_SM_STACK
+#define HJK_SM_STACK 8
+#endif
+constexpr int kSmStack = HJK_SM_STACK;  // stack entries kept in shared memory per thread
+constexpr int kLocalStack = 32 - HJK_SM_STACK;  // overflow entries in local memory
 constexpr int kMaxStack = kSmStack + kLocalStack;
 constexpr int kFetchThreshold = 20;  // refill a warp when fewer lanes than this are busy
 constexpr int kPostponeLanes = 8;    // postpone primitive tests that fewer lanes than this would run

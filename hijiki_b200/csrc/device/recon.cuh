@@ -21,11 +21,12 @@ struct PassDev {
   const int32_t* tile_block;   // [tiles_y * tiles_x] index into `blocks`, -1 = no block
   const HjkImageBlock* blocks;
   const float* weights;        // [(2R+1)^2] spatial weights per block, dx-major; < 0 = skipped tap
-  const uint32_t* taps;        // per block: count, then (2R+1)^2 x {weight bits, packed offset} of the
-                               // taps with weight >= 0 in loop order (recon_tap_stride words per block)
+  const uint32_t* taps;        // per block: {count, 0}, then (2R+1)^2 x {weight bits, packed offset} of the
+                               // taps with weight >= 0 in loop order (recon_tap_stride words per block,
+                               // 8-byte aligned pairs)
   int32_t radius;
 };
-HJK_HD uint32_t recon_tap_stride(int radius) { return 1u + 2u * (uint32_t)((2 * radius + 1) * (2 * radius + 1)); }
+HJK_HD uint32_t recon_tap_stride(int radius) { return 2u + 2u * (uint32_t)((2 * radius + 1) * (2 * radius + 1)); }
 
 // spatial weight of tap (dx, dy) for a block's sample offset — reconstruction.glsl:29-30,43-46
 HJK_HD float recon_spatial_weight(int dx, int dy, int radius, float stddev, float so_x, float so_y) {
@@ -47,11 +48,12 @@ HJK_HD void recon_fill_block_tables(const HjkImageBlock& blk, int radius, float 
       const float w = recon_spatial_weight(dx, dy, radius, stddev, blk.sample_offset[0], blk.sample_offset[1]);
       weights[(dx + radius) * t + (dy + radius)] = w;
       if (w < 0.f) continue;
-      taps[1 + 2 * n] = x::as_uint(w);
-      taps[2 + 2 * n] = (uint32_t)(dx + 128) | ((uint32_t)(dy + 128) << 8);
+      taps[2 + 2 * n] = x::as_uint(w);
+      taps[3 + 2 * n] = (uint32_t)(dx + 128) | ((uint32_t)(dy + 128) << 8);
       n++;
     }
   taps[0] = n;
+  taps[1] = 0;
 }
 
 // one tap of reconstruction.glsl:47-59: bilateral factor, NaN rejection, accumulate
@@ -64,7 +66,7 @@ HJK_HD void recon_tap(const Layers& L, uint32_t px, uint32_t py, float w, vec3 n
     const vec3 ao = xyz(L.albedo(px, py)) - ac;
     e = x::add(e, dot(ao, ao));
   }
-  if (e != 0.f) w = x::mul(w, exp_det(-e));  // exp_det(-0) == 1 exactly, so the branch only saves work
+  if (e != 0.f) w = x::mul(w, exp_det_neg(e));  // exp_det(-0) == 1 exactly, so the branch only saves work
   const f4 wv = F4(x::mul(w, cw.x), x::mul(w, cw.y), x::mul(w, cw.z), x::mul(w, cw.w));
   if (x::is_nan(wv.x) || x::is_nan(wv.y) || x::is_nan(wv.z) || x::is_nan(wv.w)) return;
   acc = F4(x::add(acc.x, wv.x), x::add(acc.y, wv.y), x::add(acc.z, wv.z), x::add(acc.w, wv.w));
@@ -106,11 +108,11 @@ HJK_HD f4 reconstruct_pixel(const PassDev& ps, const Layers& L, uint32_t gx, uin
       const uint32_t* tl = ps.taps + (size_t)b * stride;
       const uint32_t n = tl[0];
       for (uint32_t k = 0; k < n; k++) {
-        const uint32_t o = tl[2 + 2 * k];
+        const uint32_t wbits = tl[2 + 2 * k], o = tl[3 + 2 * k];  // one 8-byte load
         const int dx = (int)(o & 0xFFu) - 128, dy = (int)((o >> 8) & 0xFFu) - 128;
         const int sx = lx + dx, sy = ly + dy;
         if (sx < 0 || sy < 0 || sx >= dimx || sy >= dimy) continue;
-        recon_tap<HAS_ALBEDO>(L, (uint32_t)((int)gx + dx), (uint32_t)((int)gy + dy), x::as_float(tl[1 + 2 * k]), nc, ac,
+        recon_tap<HAS_ALBEDO>(L, (uint32_t)((int)gx + dx), (uint32_t)((int)gy + dy), x::as_float(wbits), nc, ac,
                               acc);
       }
     }

@@ -13,6 +13,7 @@
 // Box culling uses FMA and conservative (outward-rounded, padded) boxes; it never decides a
 // hit, it only skips primitives whose exact test would fail.
 #pragma once
+#include "../cwbvh.h"
 #include "scene_dev.cuh"
 
 namespace hjk {
@@ -41,6 +42,9 @@ HJK_HD uint32_t sign_extend_s8x4(uint32_t v) {
   return ((v >> 7) & 0x01010101u) * 0xFFu;
 #endif
 }
+// byte j of `word` as a float: shift/mask + I2F.  (Measured on B200: building 2^23 + byte with PRMT
+// and subtracting 2^23 is slower — it moves the conversion from the otherwise idle XU pipe onto the
+// ALU/FMA pipes the slab test already saturates.)
 HJK_HD float byte_to_float(uint32_t word, int j) { return (float)((word >> (8 * j)) & 0xFFu); }
 
 struct TravState {
@@ -174,7 +178,7 @@ HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, c
 //   quad    : shapes/quad.glsl:7-25
 // On acceptance writes t (and u, v for triangles/quads) and returns true.
 HJK_HD bool intersect_prim(const SceneDev& sc, const TravState& s, const f4& r0, const f4& r1,
-                           const f4& r2, float& t_out, float& u_out, float& v_out) {
+                           const f4& r2, const f4& r3, float& t_out, float& u_out, float& v_out) {
   const uint32_t id = x::as_uint(r0.w);
   const vec3 o = V3(s.ox, s.oy, s.oz), d = V3(s.dx, s.dy, s.dz);
   if (id < sc.num_spheres) {
@@ -198,7 +202,11 @@ HJK_HD bool intersect_prim(const SceneDev& sc, const TravState& s, const f4& r0,
     return false;
   }
   const vec3 e1 = xyz(r1), e2 = xyz(r2);
+#if HJK_PRIM_STRIDE == 4
+  const vec3 n = xyz(r3);  // precomputed cross(e1, e2), same bits
+#else
   const vec3 n = cross(e1, e2);
+#endif
   const vec3 ro = o - xyz(r0);
   const vec3 q = cross(ro, d);
   const float dd = x::div(1.0f, dot(d, n));
@@ -265,10 +273,15 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       }
       const int i = hi_bit(s.tg_y);
       s.tg_y &= ~(1u << i);
-      const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * 3;
+      const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * HJK_PRIM_STRIDE;
       const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
+#if HJK_PRIM_STRIDE == 4
+      const f4 r3 = ld16(pp + 3);
+#else
+      const f4 r3 = r2;
+#endif
       float t, u, v;
-      if (intersect_prim(sc, s, r0, r1, r2, t, u, v)) {
+      if (intersect_prim(sc, s, r0, r1, r2, r3, t, u, v)) {
         s.hit_id = (int32_t)x::as_uint(r0.w);
         s.hit_t = t, s.hit_u = u, s.hit_v = v;
         if (s.slot >> 31) return true;

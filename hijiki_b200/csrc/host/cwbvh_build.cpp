@@ -291,6 +291,16 @@ void make_prim(const HjkScene& s, uint32_t shape, WidePrim& p) {
     }
   }
   std::memcpy(&p.r0[3], &id, 4);
+#if HJK_PRIM_STRIDE == 4
+  if (shape >= S) {  // n = cross(e1, e2), each product and difference rounded to fp32 on its own
+    const float* a = p.r1;
+    const float* b = p.r2;
+    volatile float m0 = a[1] * b[2], m1 = b[1] * a[2], m2 = a[2] * b[0], m3 = b[2] * a[0], m4 = a[0] * b[1],
+                   m5 = b[0] * a[1];
+    volatile float n0 = m0 - m1, n1 = m2 - m3, n2 = m4 - m5;
+    p.r3[0] = n0, p.r3[1] = n1, p.r3[2] = n2;
+  }
+#endif
 }
 
 Box shape_box(const HjkScene& s, uint32_t shape) {
