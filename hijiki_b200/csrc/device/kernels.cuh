@@ -74,7 +74,10 @@ constexpr int kLocalStack = 32 - HJK_SM_STACK;  // overflow entries in local mem
 constexpr int kMaxStack = kSmStack + kLocalStack;
 constexpr int kFetchThreshold = 20;  // refill a warp when fewer lanes than this are busy
 constexpr int kPostponeLanes = 8;    // postpone primitive tests that fewer lanes than this would run
-constexpr int kTileThreads = 256;
+#ifndef HJK_TILE_THREADS
+#define HJK_TILE_THREADS 256
+#endif
+constexpr int kTileThreads = HJK_TILE_THREADS;
 
 // ---------------------------------------------------------------- block-level compaction
 // Every thread of the block calls this (flag may be false).  Returns the global position
@@ -305,7 +308,7 @@ struct TileSort {
   uint32_t entry[kTileThreads];
 };
 
-__global__ void __launch_bounds__(kTileThreads, 4) k_shade(WaveDev w, uint32_t bounce) {
+__global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(WaveDev w, uint32_t bounce) {
   __shared__ BlockAppend<2> sm;
   __shared__ TileSort ts;
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
