@@ -110,6 +110,11 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
   s.octinv4 = (7u - oct) * 0x01010101u;
   s.ng_x = 0;
   s.ng_y = 0x80000000u;  // "slot 7^octinv of a virtual parent with imask 0" = node 0
+  // A direction of exactly (0,0,0) is outside the contract: the reference arithmetic turns it into
+  // "hits" at t = +inf on every triangle facing the origin (1/dot(d,n) = inf, shapes/triangle.glsl:24)
+  // — an artefact no integrator ray can produce (directions come out of normalize/reflect/frame
+  // products).  Such a ray is reported as a miss: no traversal work is queued.
+  if (s.dx == 0.f && s.dy == 0.f && s.dz == 0.f) s.ng_y = 0;
   s.tg_x = s.tg_y = 0;
   s.hit_id = -1;
   s.hit_t = 0.f, s.hit_u = 0.f, s.hit_v = 0.f;

@@ -222,3 +222,82 @@ def orc_params(max_bounces=1000, rr_start=3, radius=2, stddev=0.5, eps=1e-4, use
 
 def hjk_params(max_bounces=1000, rr_start=3, radius=2, stddev=0.5, eps=1e-4, flags=0) -> _abi.HjkParams:
     return _abi.HjkParams(max_bounces, rr_start, radius, stddev, eps, flags)
+
+
+class CustomScene:
+    """A compiled scene assembled from numpy arrays in the reference's binding layouts.
+    Shape order = [spheres | quads | triangles]; `materials` = one (tag, index) pair per shape."""
+
+    def __init__(self, camera, spheres=(), quads=(), triangles=(), vertices=(), materials=(), diffuse=(),
+                 diffusecb=(), dielectric=(), emissive=()):
+        f32 = np.float32
+        self.arrays = {
+            "spheres": np.asarray(spheres, f32).reshape(-1, 4),
+            "quads": np.asarray(quads, f32).reshape(-1, 12),
+            "triangles": np.asarray(triangles, np.uint32).reshape(-1, 3),
+            "vertices": np.asarray(vertices, f32).reshape(-1, 8),
+            "diffuse": np.asarray(diffuse, f32).reshape(-1, 4),
+            "diffusecb": np.asarray(diffusecb, f32).reshape(-1, 8),
+            "dielectric": np.asarray(dielectric, f32).reshape(-1, 4),
+            "emissive": np.asarray(emissive, f32).reshape(-1, 4),
+        }
+        mats = np.array([(t << 24) | i for t, i in materials], np.uint32)
+        self.arrays["materials"] = mats
+        em_shapes = [k for k, (t, _) in enumerate(materials) if t == _abi.MAT_EMISSIVE]
+        em = np.zeros((len(em_shapes), 4), f32)
+        if em_shapes:
+            em.view(np.uint32)[:, 0] = em_shapes
+            em[:, 1] = f32(1.0) / f32(len(em_shapes))
+            em[:, 2] = np.cumsum(em[:, 1], dtype=f32)
+        self.arrays["emitters"] = em
+        self.info_struct = _abi.HjkSceneInfo()
+        pos, rot, fov = camera
+        for k in range(3):
+            self.info_struct.camera.position[k] = pos[k]
+        for k in range(4):
+            self.info_struct.camera.rotation[k] = rot[k]
+        self.info_struct.camera.fov = fov
+        self.info_struct.num_spheres = len(self.arrays["spheres"])
+        self.info_struct.num_quads = len(self.arrays["quads"])
+        self.info_struct.num_triangles = len(self.arrays["triangles"])
+        self.info_struct.num_emitters = len(em_shapes)
+        self.view = _abi.HjkScene()
+        self.view.scene = _abi.HjkArray(C.addressof(self.info_struct), 1)
+        self.view.bvh = _abi.HjkArray(None, 0)
+        for name, a in self.arrays.items():
+            a = np.ascontiguousarray(a)
+            self.arrays[name] = a
+            setattr(self.view, name, _abi.HjkArray(a.ctypes.data if a.size else None, len(a)))
+
+    @property
+    def info(self):
+        return self.info_struct
+
+    def array(self, name):
+        return self.arrays[name]
+
+
+def quad_room_scene():
+    """A closed room of six quads (checkerboard floor, diffuse walls) with an emissive quad under the
+    ceiling, a tinted-glass sphere (non-zero extinction), a mirror sphere and one diffuse triangle:
+    exercises shapes/quad.glsl, the quad emitter, DielectricMaterial::tinted and Beer-Lambert."""
+    D, CB, MI, DI, EM = _abi.MAT_DIFFUSE, _abi.MAT_DIFFUSECBOARD, _abi.MAT_MIRROR, _abi.MAT_DIELECTRIC, _abi.MAT_EMISSIVE
+    q = lambda o, e1, e2: [*o, 0, *e1, 0, *e2, 0]
+    quads = [
+        q((-1, 0, -1), (0, 0, 2), (2, 0, 0)),      # floor (normal +y)
+        q((-1, 2, -1), (2, 0, 0), (0, 0, 2)),      # ceiling (normal -y)
+        q((-1, 0, -1), (2, 0, 0), (0, 2, 0)),      # back wall (normal +z)
+        q((-1, 0, -1), (0, 2, 0), (0, 0, 2)),      # left wall (normal +x)
+        q((1, 0, -1), (0, 0, 2), (0, 2, 0)),       # right wall (normal -x)
+        q((-0.3, 1.98, -0.3), (0.6, 0, 0), (0, 0, 0.6)),  # light, facing down
+    ]
+    spheres = [(-0.4, 0.35, -0.2, 0.35), (0.45, 0.3, 0.1, 0.3)]
+    vertices = [(-0.2, 0.0, 0.6, 0, 0, 1, 0, 0), (0.3, 0.0, 0.7, 1, 0, 1, 0, 0), (0.0, 0.5, 0.5, 0, 0, 1, 0, 1)]
+    triangles = [(0, 1, 2)]
+    materials = [(DI, 0), (MI, 0), (CB, 0), (D, 0), (D, 0), (D, 1), (D, 2), (EM, 0), (D, 0)]
+    half = np.deg2rad(-6.0) / 2
+    camera = ((0.0, 1.0, 4.2), (float(np.sin(half)), 0.0, 0.0, float(np.cos(half))), 38.0)
+    return CustomScene(camera, spheres=spheres, quads=quads, triangles=triangles, vertices=vertices,
+                       materials=materials, diffuse=[(0.7, 0.7, 0.7, 0), (0.7, 0.2, 0.2, 0), (0.2, 0.6, 0.25, 0)],
+                       diffusecb=[(0.8, 0.8, 0.8, 0.25, 0.15, 0.15, 0.3, 0.25)],
+                       dielectric=[(0.9, 0.3, 0.2, 1.5)], emissive=[(12, 12, 12, 0)])
