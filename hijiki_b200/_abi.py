@@ -77,6 +77,7 @@ class HjkStats(C.Structure):
 HJK_RENDER_ASYNC = 1
 HJK_RENDER_NO_RECON = 2
 HJK_RENDER_KEEP_FEATURES = 4
+HJK_RENDER_EXACT_TIES = 8
 
 MAT_DIFFUSE, MAT_DIFFUSECBOARD, MAT_MIRROR, MAT_DIELECTRIC, MAT_EMISSIVE = range(5)
 MATERIAL_TAG_SHIFT = 24

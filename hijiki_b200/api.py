@@ -256,14 +256,15 @@ class Context:
     def frame_size(self):
         return self.get_info("width"), self.get_info("height")
 
-    def trace_first_hit(self, rays: np.ndarray, any_hit: bool = False):
+    def trace_first_hit(self, rays: np.ndarray, any_hit: bool = False, exact_ties: bool = False):
         """Parity hook: closest hit (or occlusion) of scene.glsl:97-175 on a ray batch."""
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         n = rays.size
         ids = np.empty(n, dtype=np.int32)
         t = np.empty(n, dtype=np.float32)
         uv = np.empty((n, 2), dtype=np.float32)
-        self._check(self.lib.hjk_trace_first_hit(self.ptr, as_ptr(rays), n, int(any_hit), as_ptr(ids), as_ptr(t),
+        self._check(self.lib.hjk_trace_first_hit(self.ptr, as_ptr(rays), n, int(any_hit) | (2 if exact_ties else 0),
+                                                 as_ptr(ids), as_ptr(t),
                                                  as_ptr(uv)))
         return ids, t, uv
 

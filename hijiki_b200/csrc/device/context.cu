@@ -118,6 +118,8 @@ struct HjkContext {
   DevBuf<f4> d_ray_o, d_ray_d, d_hit, d_thr, d_ext, d_layer0, d_layer1, d_sh_o, d_sh_d, d_sh_c;
   DevBuf<uint32_t> d_ext_q0, d_ext_q1, d_counters;
   DevBuf<unsigned long long> d_totals;  // paths, extension rays, shadow rays of the current call
+  DevBuf<uint32_t> d_unresolved;        // exact-tie mode: rays whose cluster outgrew the window/list
+  uint64_t unresolved_last = 0;         // ... of the last render / trace call
   DevBuf<int32_t> d_tile_block;
   DevBuf<HjkImageBlock> d_blocks;
   DevBuf<float> d_weights;
@@ -285,6 +287,8 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   HJK_CUDA(c, c->d_ext_q1.ensure(n_slots));
   const size_t n_ctr = ((size_t)prm->max_bounces + 1) * CTR_STRIDE;
   HJK_CUDA(c, c->d_counters.ensure(n_ctr));
+  HJK_CUDA(c, c->d_unresolved.ensure(1));
+  HJK_CUDA(c, cudaMemsetAsync(c->d_unresolved.p, 0, 4, c->stream));
   HJK_CUDA(c, c->d_totals.ensure(3));
   HJK_CUDA(c, cudaMemsetAsync(c->d_totals.p, 0, 3 * sizeof(unsigned long long), c->stream));
   HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
@@ -325,6 +329,8 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.eps = prm->eps;
   w.has_extinction = c->has_extinction ? 1u : 0u;
   w.fetch_threshold = c->fetch_threshold, w.postpone_lanes = c->postpone_lanes;
+  w.unresolved = c->d_unresolved.p;
+  const bool exact = (prm->flags & HJK_RENDER_EXACT_TIES) != 0;
 
   const int g_trav = grid_for(c, c->blocks_trav), g_tile = grid_for(c, c->blocks_tile);
   const int g_light = grid_for(c, c->blocks_light);
@@ -352,10 +358,14 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     for (uint32_t b = 0;; b++) {
       {
         KernelTimer t(c, stats, HJK_K_EXTEND);
-        if (guard)
-          k_trace<true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+        if (guard && exact)
+          k_trace<true, true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+        else if (guard)
+          k_trace<true, false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+        else if (exact)
+          k_trace<false, true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
         else
-          k_trace<false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+          k_trace<false, false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
         launches++;
       }
       if (b == last) break;
@@ -400,6 +410,9 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     if (stats) {
       unsigned long long totals[3] = {0, 0, 0};
       HJK_CUDA(c, cudaMemcpy(totals, c->d_totals.p, sizeof totals, cudaMemcpyDeviceToHost));
+      uint32_t unresolved = 0;
+      HJK_CUDA(c, cudaMemcpy(&unresolved, c->d_unresolved.p, 4, cudaMemcpyDeviceToHost));
+      c->unresolved_last = unresolved;
       n_paths = totals[0], n_ext = totals[1], n_sh = totals[2];
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -458,7 +471,7 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true>, kTravThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, kTravThreads, 0);
   c->blocks_trav = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
   c->blocks_tile = std::max(occ, 1);
@@ -705,26 +718,37 @@ int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int 
   HJK_CUDA(c, d_o.ensure(n));
   HJK_CUDA(c, d_d.ensure(n));
   HJK_CUDA(c, d_h.ensure(n));
-  HJK_CUDA(c, d_cur.ensure(1));
+  HJK_CUDA(c, d_cur.ensure(2));
   HJK_CUDA(c, cudaMemcpyAsync(d_o.p, ho.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
   HJK_CUDA(c, cudaMemcpyAsync(d_d.p, hd.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
-  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 4, c->stream));
+  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 8, c->stream));
   const float eps = 1e-4f;  // M_EPS, math.glsl:2
   const int g = grid_for(c, c->blocks_trav);
   const bool guard = c->scene.num_spheres != 0;
-  const uint32_t flavour = any_hit ? kAnyHitBit : 0u;
-  if (guard)
-    k_trace_batch<true><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour);
+  const uint32_t flavour = (any_hit & 1) ? kAnyHitBit : 0u;
+  const bool exact = (any_hit & 2) != 0;
+#define HJK_BATCH(G, E) \
+  k_trace_batch<G, E><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour)
+  if (guard && exact)
+    HJK_BATCH(true, true);
+  else if (guard)
+    HJK_BATCH(true, false);
+  else if (exact)
+    HJK_BATCH(false, true);
   else
-    k_trace_batch<false><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour);
+    HJK_BATCH(false, false);
+#undef HJK_BATCH
   HJK_CUDA(c, cudaGetLastError());
   std::vector<f4> hh(n);
   HJK_CUDA(c, cudaMemcpyAsync(hh.data(), d_h.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+  uint32_t cur2[2] = {0, 0};
+  HJK_CUDA(c, cudaMemcpyAsync(cur2, d_cur.p, 8, cudaMemcpyDeviceToHost, c->stream));
   HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->unresolved_last = cur2[1];
   for (size_t i = 0; i < n; i++) {
     int32_t id;
     memcpy(&id, &hh[i].x, 4);
-    if (any_hit) {
+    if (any_hit & 1) {
       shape_id[i] = id >= 0 ? 1 : 0;
     } else {
       shape_id[i] = id;
@@ -911,6 +935,7 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "blocks_per_sm_tile") *out = c->blocks_tile;
   else if (k == "wave_paths") *out = (int64_t)c->wave_paths;
   else if (k == "has_extinction") *out = c->has_extinction ? 1 : 0;
+  else if (k == "unresolved_ties") *out = (int64_t)c->unresolved_last;
   else if (k == "device") *out = c->device;
   else if (k == "width") *out = c->width;
   else if (k == "height") *out = c->height;

@@ -17,6 +17,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "recon.cuh"
 #include "shade.cuh"
 #include "traverse.cuh"
@@ -63,6 +65,7 @@ struct WaveDev {
   uint32_t has_extinction;
   uint32_t fetch_threshold;      // refill a warp when fewer lanes than this are busy
   uint32_t postpone_lanes;       // postpone primitive tests that fewer lanes than this would run
+  uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
 };
 
 constexpr int kTravThreads = 128;
@@ -235,16 +238,18 @@ struct WarpPolicy {
 
 // Persistent warps: each warp keeps its 32 lanes supplied with rays from the work range; a lane
 // whose ray finishes is refilled as soon as fewer than `fetch_threshold` lanes are busy.
-template <bool GUARD, class IO>
+template <bool GUARD, bool EXACT, class IO>
 __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io, uint32_t n,
                                                uint32_t* cursor, float eps, int fetch_threshold,
-                                               int postpone_lanes) {
+                                               int postpone_lanes, uint32_t* unresolved) {
   __shared__ uint2 sm_stack[kSmStack * kTravThreads];
   const uint32_t lane = threadIdx.x & 31u;
   DevStack st;
   st.sm = sm_stack + threadIdx.x;
   st.n = 0;
   TravState s;
+  typename std::conditional<EXACT, TieCands, NoCands>::type cands;
+  cands.reset();
   bool active = false, exhausted = false;
   for (;;) {
     if (!exhausted) {
@@ -257,6 +262,7 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
           const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
           if (i < n) {
             io.template load<GUARD>(i, s);
+            cands.reset();
             st.n = 0;
             active = true;
           }
@@ -267,8 +273,9 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
     if (active) {
       const WarpPolicy policy{!exhausted, fetch_threshold, postpone_lanes};
-      const bool done = trav_run<GUARD>(sc, s, st, eps, policy);
+      const bool done = trav_run<GUARD, EXACT>(sc, s, st, eps, policy, cands);
       if (done) {
+        if (EXACT && cands_unresolved(cands)) atomicAdd(unresolved, 1u);
         io.store(s);
         active = false;
       }
@@ -279,21 +286,22 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 
 // GUARD: the scene contains spheres (sphere guard of traverse.cuh compiled in).
 // bounce in [0, max_bounces]: extension rays of `bounce` (none at max_bounces) + shadow rays of bounce-1.
-template <bool GUARD>
+template <bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads) k_trace(WaveDev w, uint32_t bounce, uint32_t last) {
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
   const WaveIO io{w, w.ext_q[bounce & 1u], n_shadow};
-  traverse_queue<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
-                        (int)w.postpone_lanes);
+  traverse_queue<GUARD, EXACT>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
+                               (int)w.postpone_lanes, w.unresolved);
 }
-template <bool GUARD>
+// cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode)
+template <bool GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
                                                               f4* hit, uint32_t n, uint32_t* cursor, float eps,
                                                               uint32_t flavour) {
   const BatchIO io{sc, ray_o, ray_d, hit, flavour};
-  traverse_queue<GUARD>(sc, io, n, cursor, eps, kFetchThreshold, kPostponeLanes);
+  traverse_queue<GUARD, EXACT>(sc, io, n, cursor, eps, kFetchThreshold, kPostponeLanes, cursor + 1);
 }
 
 // ---------------------------------------------------------------- sort + shade

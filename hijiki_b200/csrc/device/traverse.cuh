@@ -59,6 +59,8 @@ struct TravState {
   // sphere guard (see trav_init): per-axis box inflation in t units, box-test interval
   float infl_x, infl_y, infl_z;
   float box_tmin, box_tmax_scale;
+  // exact-tie mode (see TieCands): boxes are culled against t_cull, tmax stays the ray's own
+  float t_cull;
 };
 
 HJK_HD float safe_rcp(float d) {
@@ -118,11 +120,12 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
   s.tg_x = s.tg_y = 0;
   s.hit_id = -1;
   s.hit_t = 0.f, s.hit_u = 0.f, s.hit_v = 0.f;
+  s.t_cull = x::as_float(0x7F800000u);
 }
 
 // 8 child boxes of one node against the ray interval; returns the 32-bit hit mask
 // (bits 31..24: inner children in near-to-far priority order, bits 23..0: primitives).
-template <bool GUARD>
+template <bool GUARD, bool EXACT>
 HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, const f4& q2,
                                const f4& q3, const f4& q4) {
   const uint32_t e_imask = x::as_uint(q0.w);
@@ -138,7 +141,8 @@ HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, c
   const float o1x = GUARD ? orgx + s.infl_x : orgx, o1y = GUARD ? orgy + s.infl_y : orgy,
               o1z = GUARD ? orgz + s.infl_z : orgz;
   const float box_tmin = GUARD ? s.box_tmin : s.tmin;
-  const float box_tmax = GUARD ? s.tmax * s.box_tmax_scale : s.tmax;
+  const float far_t = EXACT ? fminf(s.tmax, s.t_cull) : s.tmax;
+  const float box_tmax = GUARD ? far_t * s.box_tmax_scale : far_t;
   const bool nx = s.idx < 0.f, ny = s.idy < 0.f, nz = s.idz < 0.f;
   uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
@@ -237,6 +241,98 @@ HJK_HD bool intersect_prim(const SceneDev& sc, const TravState& s, const f4& r0,
   return false;
 }
 
+// EXACT-TIE MODE.  The reference reports, among hits closer than M_EPS to each other, whichever its
+// linear scan (scene.glsl:134-157: spheres, quads, triangles in index order, tMax = t - M_EPS after
+// every accepted hit) accepts last — a function of the primitive ORDER, not of geometry.  The
+// default traversal visits near children first and therefore may pick another member of such a
+// cluster ("ties: excluded and counted").  In exact mode the traversal never shrinks tMax; it
+// records every hit within a window of the nearest one (boxes are culled against nearest + window),
+// then sorts the cluster by shape id and replays the reference's acceptance rule on it.  Hits
+// beyond the first gap >= M_EPS cannot influence the winner (they are accepted before and
+// superseded, or rejected after), so the replay is exact unless the cluster is longer than the
+// window or the candidate list — then the ray is counted as unresolved.
+constexpr int kTieCands = 12;
+constexpr float kTieWindowEps = 8.0f;  // window = 8 * M_EPS
+struct TieCands {
+  float t[kTieCands];
+  uint32_t id[kTieCands];
+  uint32_t prim[kTieCands];
+  uint32_t n;
+  uint32_t unresolved;
+  HJK_HD void reset() { n = 0, unresolved = 0; }
+  HJK_HD void add(float tt, uint32_t i, uint32_t p) {
+    if (n < (uint32_t)kTieCands) {
+      t[n] = tt, id[n] = i, prim[n] = p;
+      n++;
+    } else {
+      unresolved = 1;
+    }
+  }
+};
+struct NoCands {  // default mode: nothing is recorded
+  HJK_HD void reset() {}
+  HJK_HD void add(float, uint32_t, uint32_t) {}
+};
+HJK_HD uint32_t cands_unresolved(const TieCands& c) { return c.unresolved; }
+HJK_HD uint32_t cands_unresolved(const NoCands&) { return 0u; }
+
+// Forward declaration (defined below with the primitive tests).
+HJK_HD bool intersect_prim(const SceneDev& sc, const TravState& s, const f4& r0, const f4& r1,
+                           const f4& r2, const f4& r3, float& t_out, float& u_out, float& v_out);
+
+// Picks the reference's winner among the recorded candidates; s.hit_* hold the nearest one on entry.
+HJK_HD void resolve_ties(const SceneDev& sc, TravState& s, TieCands& c, float eps) {
+  if (c.n <= 1u) return;
+  // selection sort by t (n <= 12)
+  for (uint32_t i = 0; i + 1 < c.n; i++) {
+    uint32_t m = i;
+    for (uint32_t k = i + 1; k < c.n; k++)
+      if (c.t[k] < c.t[m]) m = k;
+    if (m != i) {
+      const float tt = c.t[i];
+      const uint32_t ii = c.id[i], pp = c.prim[i];
+      c.t[i] = c.t[m], c.id[i] = c.id[m], c.prim[i] = c.prim[m];
+      c.t[m] = tt, c.id[m] = ii, c.prim[m] = pp;
+    }
+  }
+  // the cluster ends at the first gap: fl(t[k] - eps) >= t[k-1] means hit k can neither reject nor be
+  // rejected by anything before it
+  uint32_t g = 1;
+  while (g < c.n && !(x::sub(c.t[g], eps) >= c.t[g - 1])) g++;
+  const float window_end = x::add(c.t[0], x::mul(kTieWindowEps, eps));
+  if (g == c.n && x::add(c.t[g - 1], eps) > window_end) c.unresolved = 1;  // chain may continue past the window
+  if (g == 1u) return;  // the nearest hit stands alone
+  // replay the linear scan over the cluster in shape-id order
+  float cur = s.tmax;
+  uint32_t winner = 0xFFFFFFFFu, last_id = 0;
+  for (uint32_t step = 0; step < g; step++) {
+    uint32_t m = 0xFFFFFFFFu;
+    for (uint32_t k = 0; k < g; k++)
+      if ((step == 0 || c.id[k] > last_id) && (m == 0xFFFFFFFFu || c.id[k] < c.id[m])) m = k;
+    if (m == 0xFFFFFFFFu) break;
+    last_id = c.id[m];
+    if (c.t[m] <= cur) {
+      winner = m;
+      cur = x::sub(c.t[m], eps);
+    }
+  }
+  if (winner == 0xFFFFFFFFu || (int32_t)c.id[winner] == s.hit_id) return;
+  const f4* pp = sc.prims + (size_t)c.prim[winner] * HJK_PRIM_STRIDE;
+  const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
+#if HJK_PRIM_STRIDE == 4
+  const f4 r3 = ld16(pp + 3);
+#else
+  const f4 r3 = r2;
+#endif
+  float t, u, v;
+  if (intersect_prim(sc, s, r0, r1, r2, r3, t, u, v)) {
+    s.hit_id = (int32_t)c.id[winner];
+    s.hit_t = t, s.hit_u = u, s.hit_v = v;
+  }
+}
+
+HJK_HD void resolve_ties(const SceneDev&, TravState&, NoCands&, float) {}
+
 // Scheduling policy of the host-side harness and of single-ray callers: never yield, never postpone.
 struct TravNoPolicy {
   HJK_HD bool yield() const { return false; }
@@ -250,8 +346,9 @@ struct TravNoPolicy {
 // (only the visiting order changes, never what is accepted).
 //   Stack: push(uint32_t, uint32_t), pop(uint32_t&, uint32_t&), empty().
 // Any-hit rays (top bit of s.slot set) return at the first accepted primitive.
-template <bool GUARD, class Stack, class Policy>
-HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, const Policy& policy) {
+// EXACT: closest-hit rays record their candidates in `cands` (TieCands) and resolve ties at the end.
+template <bool GUARD, bool EXACT, class Stack, class Policy, class Cands>
+HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, const Policy& policy, Cands& cands) {
   for (;;) {
     if (s.ng_y > 0x00FFFFFFu) {
       const uint32_t hits_imask = s.ng_y;
@@ -262,7 +359,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       const uint32_t rel = (uint32_t)pop_count(hits_imask & ~(0xFFFFFFFFu << slot));
       const f4* np = sc.nodes + (size_t)(s.ng_x + rel) * 5;
       const f4 q0 = ld16(np), q1 = ld16(np + 1), q2 = ld16(np + 2), q3 = ld16(np + 3), q4 = ld16(np + 4);
-      const uint32_t hitmask = intersect_node<GUARD>(s, q0, q1, q2, q3, q4);
+      const uint32_t hitmask = intersect_node<GUARD, EXACT>(s, q0, q1, q2, q3, q4);
       s.ng_x = x::as_uint(q1.x);
       s.ng_y = (hitmask & 0xFF000000u) | (x::as_uint(q0.w) >> 24);
       s.tg_x = x::as_uint(q1.y);
@@ -278,7 +375,8 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       }
       const int i = hi_bit(s.tg_y);
       s.tg_y &= ~(1u << i);
-      const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * HJK_PRIM_STRIDE;
+      const uint32_t prim_index = s.tg_x + (uint32_t)i;
+      const f4* pp = sc.prims + (size_t)prim_index * HJK_PRIM_STRIDE;
       const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
 #if HJK_PRIM_STRIDE == 4
       const f4 r3 = ld16(pp + 3);
@@ -287,14 +385,31 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
 #endif
       float t, u, v;
       if (intersect_prim(sc, s, r0, r1, r2, r3, t, u, v)) {
-        s.hit_id = (int32_t)x::as_uint(r0.w);
-        s.hit_t = t, s.hit_u = u, s.hit_v = v;
-        if (s.slot >> 31) return true;
-        s.tmax = x::sub(t, eps);  // scene.glsl:116
+        if (s.slot >> 31) {
+          s.hit_id = (int32_t)x::as_uint(r0.w);
+          return true;
+        }
+        if (EXACT) {
+          if (t <= s.t_cull) {
+            cands.add(t, x::as_uint(r0.w), prim_index);
+            if (s.hit_id < 0 || t < s.hit_t) {
+              s.hit_id = (int32_t)x::as_uint(r0.w);
+              s.hit_t = t, s.hit_u = u, s.hit_v = v;
+              s.t_cull = x::add(t, x::mul(kTieWindowEps, eps));
+            }
+          }
+        } else {
+          s.hit_id = (int32_t)x::as_uint(r0.w);
+          s.hit_t = t, s.hit_u = u, s.hit_v = v;
+          s.tmax = x::sub(t, eps);  // scene.glsl:116
+        }
       }
     }
     if (s.ng_y <= 0x00FFFFFFu) {
-      if (stack.empty()) return true;
+      if (stack.empty()) {
+        if (EXACT && !(s.slot >> 31)) resolve_ties(sc, s, cands, eps);
+        return true;
+      }
       stack.pop(s.ng_x, s.ng_y);
     }
     if (policy.yield()) return false;

@@ -186,7 +186,11 @@ typedef struct HjkParams {
 enum {
   HJK_RENDER_ASYNC = 1u << 0,       /* return after enqueue; default waits for the device */
   HJK_RENDER_NO_RECON = 1u << 1,    /* integrate only (debug / feature export) */
-  HJK_RENDER_KEEP_FEATURES = 1u << 2 /* keep the last pass' intermediate layers for hjk_read_intermediate */
+  HJK_RENDER_KEEP_FEATURES = 1u << 2, /* keep the last pass' intermediate layers for hjk_read_intermediate */
+  HJK_RENDER_EXACT_TIES = 1u << 3     /* resolve hits closer than eps to each other exactly as the reference's
+                                         linear scan does (scene.glsl:134-157) instead of near-child-first;
+                                         slower; rays whose cluster cannot be resolved are counted in
+                                         hjk_get_info("unresolved_ties") */
 };
 
 enum { HJK_N_KERNEL_SLOTS = 8 };
@@ -257,8 +261,8 @@ HJK_API int hjk_read_intermediate(HjkContext* ctx, int layer, float* rgba);
 
 /* Parity hook (no reference analogue): closest hit of scene.glsl:97-175 on a
  * caller-supplied HOST ray batch.  shape_id = -1 on a miss (scene.glsl:98,160).
- * t/uv may be NULL.  any_hit != 0 runs the shadow-ray (occlusion) traversal
- * instead and writes 0/1 into shape_id. */
+ * t/uv may be NULL.  `any_hit` is a bit set: bit 0 runs the shadow-ray (occlusion) traversal
+ * instead and writes 0/1 into shape_id; bit 1 selects the exact-tie mode of HJK_RENDER_EXACT_TIES. */
 HJK_API int hjk_trace_first_hit(HjkContext* ctx, const HjkRay* rays, uint64_t n_rays, int any_hit,
                                 int32_t* shape_id, float* t, float* uv);
 

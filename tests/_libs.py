@@ -109,6 +109,9 @@ def hosttest() -> C.CDLL:
         L.ht_render.argtypes = [_P, _P, C.c_uint64, C.POINTER(_abi.HjkParams), _P, _P, _P]
         L.ht_denoise.restype = C.c_int
         L.ht_denoise.argtypes = [_P, C.c_uint64, C.POINTER(_abi.HjkParams), _P, _P, _P, _P]
+        L.ht_set_exact.restype = None
+        L.ht_set_exact.argtypes = [C.c_int]
+        L.ht_unresolved.restype = C.c_uint64
         L.ht_trace_path.restype = C.c_int
         L.ht_trace_path.argtypes = [_P, _P, C.c_uint32, C.c_uint32, C.POINTER(_abi.HjkParams), _P, C.c_int, _P]
         L.ht_math_eval.restype = None

@@ -49,8 +49,10 @@ struct ChaosPolicy {
 // the kernels are instantiated per scene for GUARD = "has spheres"; mirror that choice here
 template <bool ANY_HIT, class Policy>
 bool run_ray(const SceneDev& sc, TravState& s, struct HostStack& st, float eps, const Policy& p);
+thread_local TieCands g_cands;  // exact-tie mode: candidates of the ray in flight
 template <class F4>
 void init_ray(const SceneDev& sc, TravState& s, const F4& o, const F4& d) {
+  g_cands.reset();
   if (sc.num_spheres) trav_init<true>(s, sc, o, d); else trav_init<false>(s, sc, o, d);
 }
 
@@ -82,10 +84,20 @@ struct FrameLayers {
   f4 albedo(uint32_t gx, uint32_t gy) const { return at(l2, gx, gy); }
 };
 
+bool g_exact_ties = false;     // exact-tie mode of the harness (ht_set_exact)
+uint64_t g_unresolved = 0;
+
 template <bool ANY_HIT, class Policy>
 bool run_ray(const SceneDev& sc, TravState& s, HostStack& st, float eps, const Policy& p) {
   s.slot = ANY_HIT ? 0x80000000u : 0u;
-  return sc.num_spheres ? trav_run<true>(sc, s, st, eps, p) : trav_run<false>(sc, s, st, eps, p);
+  if (g_exact_ties) {
+    const bool done = sc.num_spheres ? trav_run<true, true>(sc, s, st, eps, p, g_cands)
+                                     : trav_run<false, true>(sc, s, st, eps, p, g_cands);
+    if (done && g_cands.unresolved) g_unresolved++;
+    return done;
+  }
+  NoCands none;
+  return sc.num_spheres ? trav_run<true, false>(sc, s, st, eps, p, none) : trav_run<false, false>(sc, s, st, eps, p, none);
 }
 
 }  // namespace
@@ -127,6 +139,11 @@ void* ht_create(const HjkScene* s, float pad_rel, char* err_out, int err_cap) {
   return h;
 }
 void ht_destroy(void* p) { delete (Harness*)p; }
+void ht_set_exact(int on) {
+  g_exact_ties = on != 0;
+  g_unresolved = 0;
+}
+uint64_t ht_unresolved(void) { return g_unresolved; }
 
 void ht_bvh_stats(void* p, uint64_t* n_nodes, uint64_t* n_prims, uint32_t* depth, float* sah, float* pad,
                   int* max_stack) {

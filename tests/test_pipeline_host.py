@@ -199,3 +199,63 @@ def test_sum_of_weights_interior_pixel(oracle, hosttest):
                                _libs.ptr(acc)) == 0
     assert acc[32, 32, 3] == pytest.approx(1.61158, abs=1e-4)
     assert acc[0, 0, 3] < acc[32, 32, 3]
+
+
+def _tie_heavy_rays(n=30000, seed=2):
+    """Rays dropped onto the floor under and around the teapot, whose base is coplanar with the floor:
+    many of them see two surfaces closer than M_EPS to each other (SURVEY Q1 ties)."""
+    rng = np.random.default_rng(seed)
+    rays = np.zeros(n, dtype=_abi.RAY_DTYPE)
+    rays["origin"] = np.stack([rng.random(n) * 1.2 - 0.6, rng.random(n) * 0.5 + 0.05, rng.random(n) * 1.2 - 0.6],
+                              1).astype(np.float32)
+    d = np.stack([rng.standard_normal(n) * 0.05, -np.ones(n), rng.standard_normal(n) * 0.05], 1)
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["direction"][: n // 8] = (0, -1, 0)
+    rays["t_min"], rays["t_max"] = 1e-4, np.inf
+    return rays
+
+
+def test_exact_tie_mode_reproduces_the_linear_scan_winner(oracle, hosttest, cbox):
+    """HJK_RENDER_EXACT_TIES: among hits closer than M_EPS the reference's winner depends on primitive
+    order (scene.glsl:134-157); the exact mode replays that order, so ids/t agree on EVERY ray."""
+    h = _harness(hosttest, cbox)
+    rays = _tie_heavy_rays()
+    ids_o, t_o, uv_o, tie = _trace_oracle(oracle, cbox, rays)
+    assert tie.sum() >= 10
+    ids_d, t_d, _ = _trace_harness(hosttest, h, rays)
+    assert (ids_d != ids_o).sum() > 0 and ((ids_d != ids_o) & (tie == 0)).sum() == 0  # default: ties only
+    hosttest.ht_set_exact(1)
+    try:
+        ids_e, t_e, uv_e = _trace_harness(hosttest, h, rays)
+        assert hosttest.ht_unresolved() == 0
+        ids_c, t_c, _ = _trace_harness(hosttest, h, rays, chaos=True)  # schedule-independent too
+    finally:
+        hosttest.ht_set_exact(0)
+    assert np.array_equal(ids_e, ids_o) and np.array_equal(ids_c, ids_o)
+    assert np.array_equal(t_e.view(np.uint32), t_o.view(np.uint32))
+    hit = ids_o >= 0
+    assert np.array_equal(uv_e[hit].view(np.uint32), uv_o[hit].view(np.uint32))
+    hosttest.ht_destroy(h)
+
+
+def test_exact_tie_mode_render_is_bit_identical(oracle, hosttest, cbox_spheres):
+    h = _harness(hosttest, cbox_spheres)
+    blocks = _libs.generate_blocks(hosttest, 200, 150, 2, block_size=64)
+    acc_o = np.zeros((150, 200, 4), np.float32)
+    st = _libs.OrcStats()
+    op = _libs.orc_params(max_bounces=8, use_bvh=0, block_size=64)
+    assert oracle.orc_render(C.byref(cbox_spheres.view), _libs.ptr(blocks), blocks.size, C.byref(op), _libs.ptr(acc_o),
+                             C.byref(st), 0) == 0
+    hosttest.ht_set_exact(1)
+    try:
+        acc_h = np.zeros_like(acc_o)
+        cnt = np.zeros(3, np.uint64)
+        hp = _libs.hjk_params(max_bounces=8)
+        assert hosttest.ht_render(h, _libs.ptr(blocks), blocks.size, C.byref(hp), _libs.ptr(acc_h), None,
+                                  _libs.ptr(cnt)) == 0
+        assert hosttest.ht_unresolved() == 0
+    finally:
+        hosttest.ht_set_exact(0)
+    hosttest.ht_destroy(h)
+    assert np.array_equal(acc_h.view(np.uint32), acc_o.view(np.uint32))
+    assert (int(cnt[1]), int(cnt[2])) == (st.n_extension_rays, st.n_shadow_rays)
