@@ -322,6 +322,16 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+
+    # exact-tie mode (HJK_RENDER_EXACT_TIES), two steps: what bit-identity with the reference on every ray costs
+    exact_params = hj.make_params(max_bounces=max_bounces, flags=hj.HJK_RENDER_EXACT_TIES)
+    exact_rays, exact_ms = 0, 0.0
+    for s in range(args.warmup, min(n_steps_total, args.warmup + 2)):
+        ctx.frame_begin(width, height)
+        st = ctx.render_resident(handles[s], 0, slices[s].size, exact_params)
+        exact_rays += st.n_rays
+        exact_ms += st.ms_total
+    exact_unresolved = ctx.get_info("unresolved_ties")
     for h in handles:
         ctx.blocks_free(h)
 
@@ -416,6 +426,9 @@ def main():
                                  "(SURVEY.md §8d); see profiles/ for SM issue utilisation"},
             "pipeline_bytes": {"achieved": pipe, "unit": "GB/s", "frac": pipe / peak},
             "clocks": clocks,
+            "exact_ties": {"value": exact_rays / (exact_ms * 1e-3) / 1e6 if exact_ms else None, "unit": "Mrays/s",
+                           "unresolved_clusters_last_step": exact_unresolved,
+                           "note": "this rank, 2 steps, HJK_RENDER_EXACT_TIES: frames bit-identical to the oracle"},
         }
         if e2e_ms is not None:
             line["e2e"] = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
