@@ -11,9 +11,13 @@
 //   5. child boxes quantised to 8 bits per plane, rounded outward, nodes emitted breadth-first
 //      (the children of a node are contiguous), primitives emitted in node order.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 #include "wide_bvh_host.h"
 
@@ -64,22 +68,16 @@ struct Binary {
   std::vector<uint32_t> order;  // primitive indices, subtree ranges are contiguous
 };
 
-void build_binary(const std::vector<Box>& boxes, Binary& out) {
-  const uint32_t n = (uint32_t)boxes.size();
-  out.order.resize(n);
-  for (uint32_t i = 0; i < n; i++) out.order[i] = i;
-  std::vector<float> cen((size_t)n * 3);
-  for (uint32_t i = 0; i < n; i++)
-    for (int k = 0; k < 3; k++) cen[(size_t)i * 3 + k] = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
-  out.nodes.clear();
-  out.nodes.reserve((size_t)2 * n);
-  out.nodes.emplace_back();
-  out.nodes[0].first = 0;
-  out.nodes[0].count = n;
-  std::vector<uint32_t> stack{0};
-  while (!stack.empty()) {
-    const uint32_t ni = stack.back();
-    stack.pop_back();
+// Binned-SAH binary build.  Nodes are numbered in preorder — a subtree over c primitives owns the
+// 2c-1 consecutive indices starting at its root — so subtrees can be built by independent threads
+// into disjoint index ranges, and the result does not depend on the thread count.
+struct BinaryBuilder {
+  const std::vector<Box>& boxes;
+  std::vector<float> cen;
+  Binary& out;
+
+  // Fills node `ni` (first/count already set); returns false for a leaf, else sets its children.
+  bool split(uint32_t ni) {
     const uint32_t first = out.nodes[ni].first, count = out.nodes[ni].count;
     uint32_t* idx = out.order.data() + first;
     Box nb, cb;
@@ -92,7 +90,7 @@ void build_binary(const std::vector<Box>& boxes, Binary& out) {
     out.nodes[ni].box = nb;
     if (count == 1) {
       out.nodes[ni].leaf = true;
-      continue;
+      return false;
     }
     // binned SAH over the three axes
     int best_axis = -1, best_split = -1;
@@ -151,18 +149,52 @@ void build_binary(const std::vector<Box>& boxes, Binary& out) {
       mid = (uint32_t)(m - idx);
       if (mid == 0 || mid == count) mid = count / 2;
     }
-    const uint32_t l = (uint32_t)out.nodes.size();
-    out.nodes.emplace_back();
-    out.nodes.emplace_back();
+    const uint32_t l = ni + 1, r = ni + 2 * mid;  // preorder: the left subtree owns 2*mid-1 nodes
     out.nodes[ni].left = l;
-    out.nodes[ni].right = l + 1;
+    out.nodes[ni].right = r;
     out.nodes[l].first = first;
     out.nodes[l].count = mid;
-    out.nodes[l + 1].first = first + mid;
-    out.nodes[l + 1].count = count - mid;
-    stack.push_back(l + 1);
-    stack.push_back(l);
+    out.nodes[r].first = first + mid;
+    out.nodes[r].count = count - mid;
+    return true;
   }
+
+  void build_serial(uint32_t root) {
+    std::vector<uint32_t> stack{root};
+    while (!stack.empty()) {
+      const uint32_t ni = stack.back();
+      stack.pop_back();
+      if (split(ni)) {
+        stack.push_back(out.nodes[ni].right);
+        stack.push_back(out.nodes[ni].left);
+      }
+    }
+  }
+
+  void build_parallel(uint32_t root, int depth) {
+    if (depth >= 5 || out.nodes[root].count < 65536u) {  // at most 32 concurrent subtrees
+      build_serial(root);
+      return;
+    }
+    if (!split(root)) return;
+    const uint32_t l = out.nodes[root].left, r = out.nodes[root].right;
+    std::thread other([this, l, depth]() { build_parallel(l, depth + 1); });
+    build_parallel(r, depth + 1);
+    other.join();
+  }
+};
+
+void build_binary(const std::vector<Box>& boxes, Binary& out) {
+  const uint32_t n = (uint32_t)boxes.size();
+  out.order.resize(n);
+  for (uint32_t i = 0; i < n; i++) out.order[i] = i;
+  BinaryBuilder bb{boxes, std::vector<float>((size_t)n * 3), out};
+  for (uint32_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) bb.cen[(size_t)i * 3 + k] = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
+  out.nodes.assign((size_t)2 * n - 1, Node2());
+  out.nodes[0].first = 0;
+  out.nodes[0].count = n;
+  bb.build_parallel(0, 0);
 }
 
 // Dynamic programme of the wide-tree collapse.  cost[n][i-1] = cheapest way to represent the
@@ -384,10 +416,20 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
   }
   out.pad = pad;
 
+  const bool verbose = std::getenv("HJK_BVH_VERBOSE") != nullptr;
+  auto tick = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    auto now = std::chrono::steady_clock::now();
+    if (verbose) std::fprintf(stderr, "[hjk bvh] %-18s %.2f s\n", what, std::chrono::duration<double>(now - tick).count());
+    tick = now;
+  };
+  lap("primitive boxes");
   Binary bin;
   build_binary(boxes, bin);
+  lap("binary SAH build");
   Collapse col;
   collapse_costs(bin, col);
+  lap("collapse costs");
   out.sah_cost = col.cost[0] / std::max(bin.nodes[0].box.half_area(), 1e-30f);
 
   // breadth-first emission
@@ -512,6 +554,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
     (void)n_inner;
     out.nodes[cur.wide] = wn;
   }
+  lap("emit wide nodes");
   out.n_shapes = n;
   if (S) {
     const HjkSphere* sp = (const HjkSphere*)s.spheres.ptr;
