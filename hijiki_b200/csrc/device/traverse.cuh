@@ -56,8 +56,8 @@ struct TravState {
   int32_t hit_id;        // global shape id of the current winner, -1 = none
   float hit_t, hit_u, hit_v;
   uint32_t slot;         // caller payload (path slot / ray index); top bit = any-hit ray
-  // sphere guard (see trav_init): per-axis box inflation in t units, box-test interval
-  float infl_x, infl_y, infl_z;
+  // sphere guard (see trav_init): per-ray constants of the per-node box inflation, box-test interval
+  float guard_e, guard_lo;
   float box_tmin, box_tmax_scale;
   // exact-tie mode (see TieCands): boxes are culled against t_cull, tmax stays the ray's own
   float t_cull;
@@ -75,35 +75,31 @@ HJK_HD float safe_rcp(float d) {
 // test is no longer geometric: it accepts exactly the rays whose line passes within
 //     R'^2 = r^2/s^2 + L^2 (1 - 1/s^2)          (L = |origin - centre|)
 // of the centre, and reports t' = s^2 * (true entry parameter of that ball).  To stay a superset
-// of what the reference accepts, boxes are inflated per ray by Delta >= R' - r and the box
-// interval is [0, tMax * max(1, 1/s^2)].  For |s^2 - 1| of a few ulps this degenerates to a
-// pad of ~1e-7 L^2 / r; for scenes without spheres it is switched off (triangle and quad tests
-// are homogeneous in d, hence geometric for any s).
+// of what the reference accepts, the child boxes of a node are inflated by Delta >= R' - r, with L
+// bounded by the distance from the ray origin to the farthest corner of the node (every sphere below
+// the node has its centre inside it), and the box interval is [0, tMax * max(1, 1/s^2)]:
+//     s^2 >= 1:  Delta = sqrt(r_min^2 + L^2 (1 - 1/s^2)) - r_min      s^2 < 1:  Delta = r_max (1/s - 1)
+// For |s^2 - 1| of a few ulps this degenerates to a pad of ~1e-7 L^2 / r; for scenes without spheres
+// it is compiled out (triangle and quad tests are homogeneous in d, hence geometric for any s).
 // GUARD = the scene contains spheres (a per-scene constant: kernels are instantiated for both).
 template <bool GUARD>
 HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const f4& d_tmax) {
   s.ox = o_tmin.x, s.oy = o_tmin.y, s.oz = o_tmin.z, s.tmin = o_tmin.w;
   s.dx = d_tmax.x, s.dy = d_tmax.y, s.dz = d_tmax.z, s.tmax = d_tmax.w;
   s.idx = safe_rcp(s.dx), s.idy = safe_rcp(s.dy), s.idz = safe_rcp(s.dz);
-  s.infl_x = s.infl_y = s.infl_z = 0.f;
+  s.guard_e = s.guard_lo = 0.f;
   s.box_tmin = s.tmin;
   s.box_tmax_scale = 1.0f;
   if (GUARD) {
     const float s2 = s.dx * s.dx + s.dy * s.dy + s.dz * s.dz;
-    const float lx = s.ox - sc.sph_centre[0], ly = s.oy - sc.sph_centre[1], lz = s.oz - sc.sph_centre[2];
-    const float L = sqrtf(lx * lx + ly * ly + lz * lz) + sc.sph_centre[3];
     const float inv_s2 = 1.0f / s2;
-    float delta;
     if (s2 >= 1.0f) {
-      delta = sqrtf(sc.sph_rmin * sc.sph_rmin + L * L * (1.0f - inv_s2)) - sc.sph_rmin;
+      s.guard_e = 1.0f - inv_s2;
     } else {
-      delta = sc.sph_rmax * (sqrtf(inv_s2) - 1.0f);
+      s.guard_lo = sc.sph_rmax * (sqrtf(inv_s2) - 1.0f);
     }
-    delta = delta * 1.02f + 1e-6f * (L + 1.0f);
-    if (!(delta >= 0.f)) delta = x::as_float(0x7F800000u);  // NaN / degenerate direction: no culling
-    const float ax = s.idx < 0.f ? -s.idx : s.idx, ay = s.idy < 0.f ? -s.idy : s.idy,
-                az = s.idz < 0.f ? -s.idz : s.idz;
-    s.infl_x = delta * ax, s.infl_y = delta * ay, s.infl_z = delta * az;
+    if (!(s.guard_e >= 0.f) || !(s.guard_lo >= 0.f))  // NaN / degenerate direction: no culling
+      s.guard_lo = x::as_float(0x7F800000u);
     s.box_tmin = 0.f;
     s.box_tmax_scale = (inv_s2 > 1.0f ? inv_s2 : 1.0f) * 1.000001f;
     if (!(s.box_tmax_scale >= 1.0f)) s.box_tmax_scale = x::as_float(0x7F800000u);
@@ -126,20 +122,29 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
 // 8 child boxes of one node against the ray interval; returns the 32-bit hit mask
 // (bits 31..24: inner children in near-to-far priority order, bits 23..0: primitives).
 template <bool GUARD, bool EXACT>
-HJK_HD uint32_t intersect_node(const TravState& s, const f4& q0, const f4& q1, const f4& q2,
+HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4& q0, const f4& q1, const f4& q2,
                                const f4& q3, const f4& q4) {
   const uint32_t e_imask = x::as_uint(q0.w);
-  const float adjx = x::as_float((e_imask & 0xFFu) << 23) * s.idx;
-  const float adjy = x::as_float(((e_imask >> 8) & 0xFFu) << 23) * s.idy;
-  const float adjz = x::as_float(((e_imask >> 16) & 0xFFu) << 23) * s.idz;
+  const float scx = x::as_float((e_imask & 0xFFu) << 23), scy = x::as_float(((e_imask >> 8) & 0xFFu) << 23),
+              scz = x::as_float(((e_imask >> 16) & 0xFFu) << 23);
+  const float adjx = scx * s.idx, adjy = scy * s.idy, adjz = scz * s.idz;
+  float infl_x = 0.f, infl_y = 0.f, infl_z = 0.f;
+  if (GUARD) {  // sphere guard: inflation from the farthest corner of this node's frame (see trav_init)
+    const float fx = fmaxf(fabsf(q0.x - s.ox), fabsf(fmaf(255.0f, scx, q0.x) - s.ox));
+    const float fy = fmaxf(fabsf(q0.y - s.oy), fabsf(fmaf(255.0f, scy, q0.y) - s.oy));
+    const float fz = fmaxf(fabsf(q0.z - s.oz), fabsf(fmaf(255.0f, scz, q0.z) - s.oz));
+    const float L2 = fx * fx + fy * fy + fz * fz;
+    float delta = fmaxf(sqrtf(fmaf(L2, s.guard_e, sc.sph_rmin * sc.sph_rmin)) - sc.sph_rmin, s.guard_lo);
+    delta = fmaf(delta, 1.02f, 1e-6f * (fx + fy + fz + 1.0f));
+    if (!(delta >= 0.f)) delta = x::as_float(0x7F800000u);
+    infl_x = delta * fabsf(s.idx), infl_y = delta * fabsf(s.idy), infl_z = delta * fabsf(s.idz);
+  }
   const float orgx = (q0.x - s.ox) * s.idx;
   const float orgy = (q0.y - s.oy) * s.idy;
   const float orgz = (q0.z - s.oz) * s.idz;
   // near planes move towards the origin, far planes away from it, by the sphere-guard inflation
-  const float o0x = GUARD ? orgx - s.infl_x : orgx, o0y = GUARD ? orgy - s.infl_y : orgy,
-              o0z = GUARD ? orgz - s.infl_z : orgz;
-  const float o1x = GUARD ? orgx + s.infl_x : orgx, o1y = GUARD ? orgy + s.infl_y : orgy,
-              o1z = GUARD ? orgz + s.infl_z : orgz;
+  const float o0x = orgx - infl_x, o0y = orgy - infl_y, o0z = orgz - infl_z;
+  const float o1x = orgx + infl_x, o1y = orgy + infl_y, o1z = orgz + infl_z;
   const float box_tmin = GUARD ? s.box_tmin : s.tmin;
   const float far_t = EXACT ? fminf(s.tmax, s.t_cull) : s.tmax;
   const float box_tmax = GUARD ? far_t * s.box_tmax_scale : far_t;
@@ -359,7 +364,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       const uint32_t rel = (uint32_t)pop_count(hits_imask & ~(0xFFFFFFFFu << slot));
       const f4* np = sc.nodes + (size_t)(s.ng_x + rel) * 5;
       const f4 q0 = ld16(np), q1 = ld16(np + 1), q2 = ld16(np + 2), q3 = ld16(np + 3), q4 = ld16(np + 4);
-      const uint32_t hitmask = intersect_node<GUARD, EXACT>(s, q0, q1, q2, q3, q4);
+      const uint32_t hitmask = intersect_node<GUARD, EXACT>(sc, s, q0, q1, q2, q3, q4);
       s.ng_x = x::as_uint(q1.x);
       s.ng_y = (hitmask & 0xFF000000u) | (x::as_uint(q0.w) >> 24);
       s.tg_x = x::as_uint(q1.y);
