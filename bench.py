@@ -58,6 +58,9 @@ EXTEND_BYTES_PER_RAY = 4 + 32 + 16
 SHADOW_BYTES_PER_RAY = 32 + 16
 PIPE_BYTES_EXT, PIPE_BYTES_SHADOW = 192, 96
 RECON_BYTES_PER_PX = 64  # 2 x 16 B layers + accumulator read + write (the all-zero albedo layer is elided)
+# dram__bytes_read.sum + dram__bytes_write.sum of k_trace per traced ray, from the ncu --set full capture of
+# one whole wave in profiles/r01b_ncu_full_selected.csv (17.57 GB over its nine k_trace launches, 216 M rays)
+TRACE_DRAM_BYTES_PER_RAY_NCU = 81.3
 
 
 def measured_peaks():
@@ -205,7 +208,7 @@ def run_reference(args, rank, wl):
 
 
 def cpu_baseline_sample(wl):
-    """Bounded CPU sample for the main line (rank 0, N = 1): ~15 s of oracle work."""
+    """Bounded CPU sample for the main line (rank 0, N = 1): ~20 s of oracle work."""
     label, kind, width, height = wl[:4]
     if kind == "terrain":
         return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port",
@@ -214,7 +217,7 @@ def cpu_baseline_sample(wl):
     mid = bpp // 2
     _, dt = run(blocks[mid:mid + 2])
     per_block = max(dt / 2, 1e-4)
-    nb = int(min(len(blocks), max(2, 15.0 / per_block)))
+    nb = int(min(len(blocks), max(2, 20.0 / per_block)))
     rays, dt = run(blocks[:nb])
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
             "sample": f"first {nb} ImageBlocks ({nb / bpp:.1f} sample passes of {width}x{height}) of the job, "
@@ -417,7 +420,12 @@ def main():
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
             "roofline": {"kernel": "k_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": (TRACE_DRAM_BYTES_PER_RAY_NCU * rays / world / n_ext_launches
+                                     if kind == "cbox" and n_ext_launches else None),
+                         "algorithmic_bytes_per_launch": trace_bytes / n_ext_launches if n_ext_launches else None,
+                         "traffic_source": "ncu DRAM bytes per traced ray (profiles/r01b, cbox) x rays per launch",
+                         "peak_source": peak_src,
                          "bytes_per_ray": {"extension": EXTEND_BYTES_PER_RAY, "shadow": SHADOW_BYTES_PER_RAY},
                          "launches": n_ext_launches,
                          "avg_launch_ms": ext_ms / n_ext_launches if n_ext_launches else None,

@@ -1,4 +1,6 @@
 """Scratch: reconstruction-only timing on 4K synthetic feature buffers (configs[4])."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, hijiki_b200 as hj, sys
 dw,dh=3840,2160
 rng=np.random.default_rng(5)

@@ -1,4 +1,6 @@
 """Scratch: cost of the exact-tie mode on cbox1080."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hijiki_b200 as hj
 W,H,spp=1920,1080,32
 ctx=hj.Context(0); ctx.scene_upload(hj.Scene.from_obj('scenes/cbox/cbox.obj').compile()); ctx.set_profiling(True)

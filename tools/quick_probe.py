@@ -1,4 +1,6 @@
 """Scratch: quick throughput probe for a library variant (HIJIKI_B200_LIB)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys, os, time
 import hijiki_b200 as hj
 which=sys.argv[1] if len(sys.argv)>1 else 'cbox'

@@ -1,4 +1,6 @@
 """Scratch perf sweep (not part of the product): kernel breakdown of cbox1080 under option settings."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys, json, itertools
 import numpy as np
 import hijiki_b200 as hj
