@@ -93,6 +93,8 @@ struct HjkContext {
   size_t ev_used = 0;
   int n_sms = 0;
   int blocks_trav = 0, blocks_tile = 0;  // resident CTAs per SM of the persistent kernels (traverse / shade)
+  int blocks_trav_v[2][2] = {{0, 0}, {0, 0}};  // ... per k_trace variant [sphere guard][exact ties]
+  int blocks_trav_override = 0;               // option blocks_per_sm_traverse
   int blocks_light = 0;                  // ... of the light tile kernels (raygen, bin)
   std::string error;
   bool profiling = false;
@@ -331,10 +333,10 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.fetch_threshold = c->fetch_threshold, w.postpone_lanes = c->postpone_lanes;
   w.unresolved = c->d_unresolved.p;
   const bool exact = (prm->flags & HJK_RENDER_EXACT_TIES) != 0;
-
-  const int g_trav = grid_for(c, c->blocks_trav), g_tile = grid_for(c, c->blocks_tile);
-  const int g_light = grid_for(c, c->blocks_light);
   const bool guard = c->scene.num_spheres != 0;
+  const int g_trav = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_trav_v[guard][exact]);
+  const int g_tile = grid_for(c, c->blocks_tile);
+  const int g_light = grid_for(c, c->blocks_light);
   uint64_t n_ext = 0, n_sh = 0, n_paths = 0;
   c->h_counters.resize(n_ctr);
   // with the reference's bounce limit (1000) paths die by roulette long before the limit:
@@ -471,8 +473,15 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, false>, kTravThreads, 0);
+  c->blocks_trav_v[0][0] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true>, kTravThreads, 0);
+  c->blocks_trav_v[0][1] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false>, kTravThreads, 0);
+  c->blocks_trav_v[1][0] = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, kTravThreads, 0);
-  c->blocks_trav = std::max(occ, 1);
+  c->blocks_trav_v[1][1] = std::max(occ, 1);
+  c->blocks_trav = c->blocks_trav_v[0][0];
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
   c->blocks_tile = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
@@ -913,7 +922,7 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
     c->postpone_lanes = (uint32_t)value;
   } else if (k == "blocks_per_sm_traverse") {
     if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
-    c->blocks_trav = (int)value;
+    c->blocks_trav_override = (int)value;
   } else if (k == "blocks_per_sm_tile") {
     if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->blocks_tile = (int)value;
@@ -931,7 +940,7 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "bvh_prims") *out = (int64_t)c->n_prims;
   else if (k == "bvh_depth") *out = c->bvh_host_stats.depth;
   else if (k == "bvh_bytes") *out = (int64_t)(c->n_nodes * sizeof(WideNode) + c->n_prims * sizeof(WidePrim));
-  else if (k == "blocks_per_sm_traverse") *out = c->blocks_trav;
+  else if (k == "blocks_per_sm_traverse") *out = c->blocks_trav_override ? c->blocks_trav_override : c->blocks_trav;
   else if (k == "blocks_per_sm_tile") *out = c->blocks_tile;
   else if (k == "wave_paths") *out = (int64_t)c->wave_paths;
   else if (k == "has_extinction") *out = c->has_extinction ? 1 : 0;

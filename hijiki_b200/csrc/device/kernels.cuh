@@ -68,6 +68,9 @@ struct WaveDev {
   uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
 };
 
+#ifndef HJK_TRACE_MIN_BLOCKS
+#define HJK_TRACE_MIN_BLOCKS 9 /* 56 registers, no spills: 36 warps per SM (measured best of 8/9/10/12) */
+#endif
 constexpr int kTravThreads = 128;
 #ifndef HJK_SM_STACK
 #define HJK_SM_STACK 8
@@ -90,7 +93,9 @@ struct BlockAppend {
   uint32_t warp_total[NQ][kTileThreads / 32];
   uint32_t base[NQ];
 };
-template <int NQ>
+// TRAILING_SYNC = false when the caller passes at least one other block barrier before it calls
+// block_append again (the shared scratch is then already safe to overwrite).
+template <int NQ, bool TRAILING_SYNC = true>
 __device__ __forceinline__ void block_append(BlockAppend<NQ>& sm, const bool (&flag)[NQ],
                                              uint32_t* const (&counter)[NQ], uint32_t (&pos)[NQ]) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -114,7 +119,7 @@ __device__ __forceinline__ void block_append(BlockAppend<NQ>& sm, const bool (&f
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < NQ; q++) pos[q] = sm.base[q] + sm.warp_total[q][warp] + prefix[q];
-  __syncthreads();  // sm is reused by the next tile
+  if (TRAILING_SYNC) __syncthreads();  // sm is reused by the next tile
 }
 
 // ---------------------------------------------------------------- raygen
@@ -286,8 +291,11 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 
 // GUARD: the scene contains spheres (sphere guard of traverse.cuh compiled in).
 // bounce in [0, max_bounces]: extension rays of `bounce` (none at max_bounces) + shadow rays of bounce-1.
+// Without the sphere guard the kernel fits 56 registers (9 CTAs = 36 warps per SM, measured best of
+// 8/9/10/12); the guard variants would spill at 56 and keep 64 registers (8 CTAs).
 template <bool GUARD, bool EXACT>
-__global__ void __launch_bounds__(kTravThreads) k_trace(WaveDev w, uint32_t bounce, uint32_t last) {
+__global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS)
+    k_trace(WaveDev w, uint32_t bounce, uint32_t last) {
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const
 // their queues by block-level compaction.
 struct TileSort {
   uint32_t warp_count[5][kTileThreads / 32];
-  uint32_t tag_base[6];
+  uint32_t n_hits;
   uint32_t entry[kTileThreads];
 };
 
@@ -342,22 +350,21 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
       if (lane == 0) ts.warp_count[t][warp] = __popc(b);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {  // exclusive scan of the 5 x 8 warp counts, tag-major
       uint32_t total = 0;
       for (uint32_t t = 0; t < 5; t++) {
-        ts.tag_base[t] = total;
         for (uint32_t wi = 0; wi < kTileThreads / 32; wi++) {
           const uint32_t c = ts.warp_count[t][wi];
           ts.warp_count[t][wi] = total;
           total += c;
         }
       }
-      ts.tag_base[5] = total;
+      ts.n_hits = total;
     }
     __syncthreads();
     if (tag < 5u) ts.entry[ts.warp_count[tag][warp] + prefix] = entry;
     __syncthreads();
-    const uint32_t n_hits = ts.tag_base[5];
+    const uint32_t n_hits = ts.n_hits;
 
     // ---- one bounce-loop iteration per hit
     bool want_next = false, want_shadow = false;
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
     const bool flag[2] = {want_next, want_shadow};
     uint32_t* const c[2] = {ctr + CTR_STRIDE + CTR_EXT, ctr + CTR_SHADOW};
     uint32_t pos[2];
-    block_append<2>(sm, flag, c, pos);  // ends with a barrier: ts may be overwritten by the next tile
+    block_append<2, false>(sm, flag, c, pos);  // the next tile's sort barriers protect `sm` and `ts`
     if (want_next) next_q[pos[0]] = slot | (out.was_discrete ? 0x80000000u : 0u);
     if (want_shadow) {
       w.sh_o[pos[1]] = out.sh_o;
