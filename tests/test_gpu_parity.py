@@ -308,3 +308,23 @@ def test_exact_tie_mode_matches_reference_on_every_ray(gpu_ctx):
             assert (st.n_extension_rays, st.n_shadow_rays) == (ost.n_extension_rays, ost.n_shadow_rays)
         else:
             assert diff.sum() <= 25 * unresolved
+
+
+def test_async_render_then_synchronize(gpu_ctx):
+    """HJK_RENDER_ASYNC returns after enqueue (the reference's render() never waits for the device either,
+    src/main.rs:1487-1490); synchronize + readback then see the finished frame."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h = 160, 96
+    blocks = hj.ImageBlockGenerator(w, h, 64, 2).blocks()
+    gpu_ctx.frame_begin(w, h)
+    gpu_ctx.render(blocks, hj.make_params(max_bounces=6))
+    want = gpu_ctx.readback(normalise=False)
+    gpu_ctx.frame_begin(w, h)
+    assert gpu_ctx.render(blocks, hj.make_params(max_bounces=6, flags=hj.HJK_RENDER_ASYNC), want_stats=False) is None
+    gpu_ctx.synchronize()
+    assert np.array_equal(gpu_ctx.readback(normalise=False), want)
+    # two renders into the same frame accumulate (src/main.rs:1330: the reconstruction ADDS)
+    gpu_ctx.render(blocks, hj.make_params(max_bounces=6), want_stats=False)
+    twice = gpu_ctx.readback(normalise=False)
+    assert np.allclose(twice, 2 * want, rtol=1e-6)
