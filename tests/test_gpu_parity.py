@@ -328,3 +328,34 @@ def test_async_render_then_synchronize(gpu_ctx):
     gpu_ctx.render(blocks, hj.make_params(max_bounces=6), want_stats=False)
     twice = gpu_ctx.readback(normalise=False)
     assert np.allclose(twice, 2 * want, rtol=1e-6)
+
+
+def test_converged_image_matches_reference_statistically(gpu_ctx):
+    """North-star image bar: with DIFFERENT block seeds and sub-pixel offsets (so no sample is shared) the
+    CUDA image and the oracle image estimate the same radiance: mean relative error of the frame mean
+    < 1 %, and the per-pixel RMSE relative to the mean radiance is what two independent 256-spp estimates
+    of this scene give each other (measured between two oracle runs) within 25 %."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h, bs, spp, bounces = 96, 72, 64, 256, 8
+    O = _libs.oracle()
+
+    def oracle_image(seed):
+        blocks = hj.ImageBlockGenerator(w, h, bs, spp, root_seed=seed).blocks()
+        acc = np.zeros((h, w, 4), np.float32)
+        op = _libs.orc_params(max_bounces=bounces, use_bvh=1, block_size=bs)
+        assert O.orc_render(C.byref(compiled.view), _libs.ptr(blocks), blocks.size, C.byref(op), _libs.ptr(acc), None,
+                            0) == 0
+        return acc[..., :3] / acc[..., 3:4]
+
+    ref_a, ref_b = oracle_image(11), oracle_image(22)
+    gpu_ctx.frame_begin(w, h)
+    gpu_ctx.render(hj.ImageBlockGenerator(w, h, bs, spp, root_seed=33).blocks(), hj.make_params(max_bounces=bounces))
+    img = gpu_ctx.readback(normalise=True)[..., :3]
+    mean = float(ref_a.mean())
+    rmse_refs = float(np.sqrt(np.mean((ref_a - ref_b) ** 2))) / mean
+    rmse_gpu = float(np.sqrt(np.mean((img - ref_a) ** 2))) / mean
+    mre = abs(float(img.mean()) - mean) / mean
+    print(f"relative RMSE oracle/oracle {rmse_refs:.4f}, cuda/oracle {rmse_gpu:.4f}; mean relative error {mre:.5f}")
+    assert mre < 0.01
+    assert rmse_gpu < 1.25 * rmse_refs + 1e-3
