@@ -1,0 +1,406 @@
+// GPU builder of the 8-wide compressed BVH (cwbvh.h) — SURVEY.md §8(f)-1: stands in for the
+// reference's host-side `bvh::BVH::build` (src/main.rs:199) when setup time matters (10 M triangles:
+// tens of milliseconds instead of seconds on the host).
+//
+//   1. k_shape_boxes   per-shape fp32 boxes (same Bounded rules as host/cwbvh_build.cpp), scene bounds
+//   2. k_morton        outward pad, 63-bit Morton code of the box centre
+//   3. cub::DeviceRadixSort::SortPairs
+//   4. k_radix_tree    binary radix tree over the sorted codes (Karras 2012), one thread per inner node
+//   5. k_fit_boxes     bottom-up box fitting + subtree sizes (second arriver continues upward)
+//   6. k_collapse      level by level: a wide node pulls up to 8 children out of its binary subtree by
+//                      repeatedly opening the child of largest area; subtrees of <= 3 primitives become
+//                      leaves; slots by octant order; 8-bit quantisation rounded outward; primitive
+//                      records written with the reference's separately rounded differences
+//
+// Tree quality is LBVH-grade (no SAH sweep): traversal is slower than with the host builder, so the
+// host builder stays the default; select this one with hjk_set_option("bvh_builder", 1).  Hit results
+// do not depend on the tree (ties excepted), so every parity test also runs against this builder.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../cwbvh.h"
+#include "scene_dev.cuh"
+
+namespace hjk {
+namespace gpubvh {
+
+struct BuildScene {
+  const f4* spheres;
+  const f4* quads;
+  const uint32_t* triangles;
+  const f4* vertices;
+  uint32_t S, Q, T;
+};
+
+constexpr uint32_t kLeafFlag = 0x80000000u;
+
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__device__ __forceinline__ void shape_box(const BuildScene& s, uint32_t shape, float lo[3], float hi[3]) {
+  if (shape < s.S) {  // src/shape.rs:13-20
+    const f4 sp = s.spheres[shape];
+    const float r = fabsf(sp.w);
+    lo[0] = sp.x - r, lo[1] = sp.y - r, lo[2] = sp.z - r;
+    hi[0] = sp.x + r, hi[1] = sp.y + r, hi[2] = sp.z + r;
+  } else if (shape < s.S + s.Q) {  // src/shape.rs:46-53
+    const f4* q = s.quads + 3 * (size_t)(shape - s.S);
+    const f4 o = q[0], e1 = q[1], e2 = q[2];
+    const float ox[3] = {o.x, o.y, o.z}, a[3] = {e1.x, e1.y, e1.z}, b[3] = {e2.x, e2.y, e2.z};
+    for (int k = 0; k < 3; k++) {
+      const float p0 = ox[k], p1 = __fadd_rn(ox[k], a[k]), p2 = __fadd_rn(ox[k], b[k]),
+                  p3 = __fadd_rn(__fadd_rn(ox[k], a[k]), b[k]);
+      lo[k] = fminf(fminf(p0, p1), fminf(p2, p3));
+      hi[k] = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+    }
+  } else {  // src/main.rs:74-79
+    const uint32_t* t = s.triangles + 3 * (size_t)(shape - s.S - s.Q);
+    const f4 a = s.vertices[2 * (size_t)t[0]], b = s.vertices[2 * (size_t)t[1]], c = s.vertices[2 * (size_t)t[2]];
+    lo[0] = fminf(a.x, fminf(b.x, c.x)), lo[1] = fminf(a.y, fminf(b.y, c.y)), lo[2] = fminf(a.z, fminf(b.z, c.z));
+    hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)), hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)), hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+  }
+}
+
+// bounds: 6 ordered uints (min xyz, max xyz), initialised to 0xFFFFFFFF x3, 0 x3
+__global__ void k_shape_boxes(BuildScene s, uint32_t n, f4* blo, f4* bhi, uint32_t* bounds, uint32_t* bad) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float lo[3], hi[3];
+    shape_box(s, i, lo, hi);
+    blo[i] = F4(lo[0], lo[1], lo[2], 0.f);
+    bhi[i] = F4(hi[0], hi[1], hi[2], 0.f);
+    for (int k = 0; k < 3; k++) {
+      if (!isfinite(lo[k]) || !isfinite(hi[k])) atomicExch(bad, 1u);
+      mn[k] = fminf(mn[k], lo[k]);
+      mx[k] = fmaxf(mx[k], hi[k]);
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xFFFFFFFFu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xFFFFFFFFu, mx[k], o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn[k] <= mx[k]) {
+      atomicMin(bounds + k, float_to_ordered(mn[k]));
+      atomicMax(bounds + 3 + k, float_to_ordered(mx[k]));
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {  // 21 bits -> every third bit
+  uint64_t x = v & 0x1FFFFFu;
+  x = (x | (x << 32)) & 0x1F00000000FFFFull;
+  x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void k_morton(uint32_t n, const uint32_t* bounds, float pad_rel, f4* blo, f4* bhi, uint64_t* keys,
+                         uint32_t* vals, float* pad_out) {
+  float smin[3], smax[3], ext = 0.f, mag = 0.f;
+  for (int k = 0; k < 3; k++) {
+    smin[k] = ordered_to_float(bounds[k]);
+    smax[k] = ordered_to_float(bounds[3 + k]);
+    ext = fmaxf(ext, smax[k] - smin[k]);
+    mag = fmaxf(mag, fmaxf(fabsf(smin[k]), fabsf(smax[k])));
+  }
+  const float pad = pad_rel * fmaxf(ext, mag);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *pad_out = pad;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    f4 lo = blo[i], hi = bhi[i];
+    lo.x -= pad, lo.y -= pad, lo.z -= pad;
+    hi.x += pad, hi.y += pad, hi.z += pad;
+    blo[i] = lo;
+    bhi[i] = hi;
+    const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    uint32_t q[3];
+    for (int k = 0; k < 3; k++) {
+      const float e = smax[k] - smin[k];
+      float u = e > 0.f ? (c[k] - smin[k]) / e : 0.5f;
+      u = fminf(fmaxf(u, 0.f), 1.f);
+      q[k] = (uint32_t)fminf(u * 2097152.0f, 2097151.0f);
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = i;
+  }
+}
+
+// common-prefix length of sorted keys i and j (ties broken by position), -1 outside [0, n)
+__device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clzll((long long)(a ^ b));
+}
+
+// Karras 2012: inner node i covers a range of sorted leaves; children carry kLeafFlag when leaves.
+__global__ void k_radix_tree(int n, const uint64_t* keys, uint32_t* child_l, uint32_t* child_r, uint32_t* parent_inner,
+                             uint32_t* parent_leaf) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+      if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+      t = (t + 1) >> 1;
+      if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const uint32_t cl = (lo == gamma) ? ((uint32_t)gamma | kLeafFlag) : (uint32_t)gamma;
+    const uint32_t cr = (hi == gamma + 1) ? ((uint32_t)(gamma + 1) | kLeafFlag) : (uint32_t)(gamma + 1);
+    child_l[i] = cl;
+    child_r[i] = cr;
+    if (cl & kLeafFlag) parent_leaf[gamma] = (uint32_t)i; else parent_inner[gamma] = (uint32_t)i;
+    if (cr & kLeafFlag) parent_leaf[gamma + 1] = (uint32_t)i; else parent_inner[gamma + 1] = (uint32_t)i;
+    if (i == 0) parent_inner[0] = 0xFFFFFFFFu;
+  }
+}
+
+// One thread per leaf walks up; the second thread to reach an inner node fits its box and goes on.
+__global__ void k_fit_boxes(int n, const uint32_t* vals, const f4* blo, const f4* bhi, const uint32_t* child_l,
+                            const uint32_t* child_r, const uint32_t* parent_inner, const uint32_t* parent_leaf,
+                            uint32_t* visits, f4* ilo, f4* ihi, uint32_t* icount) {
+  for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n; leaf += gridDim.x * blockDim.x) {
+    uint32_t node = parent_leaf[leaf];
+    while (node != 0xFFFFFFFFu) {
+      __threadfence();
+      if (atomicAdd(visits + node, 1u) == 0u) break;  // first arriver: the sibling subtree is not done yet
+      __threadfence();
+      const uint32_t cl = child_l[node], cr = child_r[node];
+      f4 llo, lhi, rlo, rhi;
+      uint32_t lc, rc;
+      // inner children were written by other threads: read them around the caches (volatile), after
+      // the fence that follows the atomic
+      auto load_inner = [&](uint32_t r, f4& o_lo, f4& o_hi, uint32_t& o_cnt) {
+        const volatile float* pl = reinterpret_cast<const volatile float*>(ilo + r);
+        const volatile float* ph = reinterpret_cast<const volatile float*>(ihi + r);
+        o_lo = F4(pl[0], pl[1], pl[2], 0.f);
+        o_hi = F4(ph[0], ph[1], ph[2], 0.f);
+        o_cnt = *reinterpret_cast<const volatile uint32_t*>(icount + r);
+      };
+      if (cl & kLeafFlag) {
+        const uint32_t p = vals[cl & ~kLeafFlag];
+        llo = blo[p], lhi = bhi[p], lc = 1;
+      } else {
+        load_inner(cl, llo, lhi, lc);
+      }
+      if (cr & kLeafFlag) {
+        const uint32_t p = vals[cr & ~kLeafFlag];
+        rlo = blo[p], rhi = bhi[p], rc = 1;
+      } else {
+        load_inner(cr, rlo, rhi, rc);
+      }
+      ilo[node] = F4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+      ihi[node] = F4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+      icount[node] = lc + rc;
+      node = parent_inner[node];
+    }
+  }
+}
+
+struct TreeDev {
+  const uint32_t* vals;     // sorted position -> shape id
+  const f4* blo;            // padded shape boxes, by shape id
+  const f4* bhi;
+  const uint32_t* child_l;  // inner nodes
+  const uint32_t* child_r;
+  const f4* ilo;
+  const f4* ihi;
+  const uint32_t* icount;
+};
+
+__device__ __forceinline__ void ref_box(const TreeDev& t, uint32_t ref, float lo[3], float hi[3], uint32_t& count) {
+  f4 a, b;
+  if (ref & kLeafFlag) {
+    const uint32_t p = t.vals[ref & ~kLeafFlag];
+    a = t.blo[p], b = t.bhi[p], count = 1;
+  } else {
+    a = t.ilo[ref], b = t.ihi[ref], count = t.icount[ref];
+  }
+  lo[0] = a.x, lo[1] = a.y, lo[2] = a.z;
+  hi[0] = b.x, hi[1] = b.y, hi[2] = b.z;
+}
+
+__device__ __forceinline__ void write_prim(const BuildScene& s, uint32_t shape, WidePrim* out) {
+  WidePrim p;
+  for (int k = 0; k < 4; k++) p.r0[k] = p.r1[k] = p.r2[k] = 0.f;
+#if HJK_PRIM_STRIDE == 4
+  for (int k = 0; k < 4; k++) p.r3[k] = 0.f;
+#endif
+  if (shape < s.S) {
+    const f4 sp = s.spheres[shape];
+    p.r0[0] = sp.x, p.r0[1] = sp.y, p.r0[2] = sp.z;
+    p.r1[0] = sp.w;
+  } else if (shape < s.S + s.Q) {
+    const f4* q = s.quads + 3 * (size_t)(shape - s.S);
+    p.r0[0] = q[0].x, p.r0[1] = q[0].y, p.r0[2] = q[0].z;
+    p.r1[0] = q[1].x, p.r1[1] = q[1].y, p.r1[2] = q[1].z;
+    p.r2[0] = q[2].x, p.r2[1] = q[2].y, p.r2[2] = q[2].z;
+  } else {
+    const uint32_t* t = s.triangles + 3 * (size_t)(shape - s.S - s.Q);
+    const f4 a = s.vertices[2 * (size_t)t[0]], b = s.vertices[2 * (size_t)t[1]], c = s.vertices[2 * (size_t)t[2]];
+    p.r0[0] = a.x, p.r0[1] = a.y, p.r0[2] = a.z;
+    // separately rounded fp32 differences, exactly what shapes/triangle.glsl:19-20 computes
+    p.r1[0] = __fsub_rn(b.x, a.x), p.r1[1] = __fsub_rn(b.y, a.y), p.r1[2] = __fsub_rn(b.z, a.z);
+    p.r2[0] = __fsub_rn(c.x, a.x), p.r2[1] = __fsub_rn(c.y, a.y), p.r2[2] = __fsub_rn(c.z, a.z);
+  }
+#if HJK_PRIM_STRIDE == 4
+  if (shape >= s.S) {
+    p.r3[0] = __fsub_rn(__fmul_rn(p.r1[1], p.r2[2]), __fmul_rn(p.r2[1], p.r1[2]));
+    p.r3[1] = __fsub_rn(__fmul_rn(p.r1[2], p.r2[0]), __fmul_rn(p.r2[2], p.r1[0]));
+    p.r3[2] = __fsub_rn(__fmul_rn(p.r1[0], p.r2[1]), __fmul_rn(p.r2[0], p.r1[1]));
+  }
+#endif
+  p.r0[3] = __uint_as_float(shape);
+  *out = p;
+}
+
+// counters: [0] wide nodes allocated, [1] primitive records allocated, [2] overflow flag
+// One thread per wide node of the current level.
+__global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const uint32_t* n_in, uint2* tasks_out,
+                           uint32_t* n_out, WideNode* nodes, WidePrim* prims, uint32_t* counters, uint32_t node_capacity) {
+  const uint32_t n_tasks = *n_in;
+  for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n_tasks; ti += gridDim.x * blockDim.x) {
+    const uint32_t wide = tasks_in[ti].x, root = tasks_in[ti].y;
+    uint32_t ref[8], cnt[8];
+    float area[8];
+    float lo[8][3], hi[8][3];
+    int ne = 2;
+    ref[0] = t.child_l[root], ref[1] = t.child_r[root];
+    for (int k = 0; k < 2; k++) {
+      ref_box(t, ref[k], lo[k], hi[k], cnt[k]);
+      const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
+      area[k] = dx * dy + dy * dz + dz * dx;
+    }
+    while (ne < 8) {  // open the largest child that is still a subtree of more than 3 primitives
+      int best = -1;
+      for (int k = 0; k < ne; k++)
+        if (cnt[k] > kWideMaxLeafPrims && (best < 0 || area[k] > area[best])) best = k;
+      if (best < 0) break;
+      const uint32_t r = ref[best];
+      const uint32_t pair[2] = {t.child_l[r], t.child_r[r]};
+      const int at[2] = {best, ne};
+      for (int c = 0; c < 2; c++) {
+        const int k = at[c];
+        ref[k] = pair[c];
+        ref_box(t, ref[k], lo[k], hi[k], cnt[k]);
+        const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
+        area[k] = dx * dy + dy * dz + dz * dx;
+      }
+      ne++;
+    }
+    // node box, slot assignment (greedy on sum of dot(child centre - node centre, slot signs))
+    float nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = 0; k < ne; k++)
+      for (int a = 0; a < 3; a++) nlo[a] = fminf(nlo[a], lo[k][a]), nhi[a] = fmaxf(nhi[a], hi[k][a]);
+    int child_in_slot[8];
+    for (int sl = 0; sl < 8; sl++) child_in_slot[sl] = -1;
+    uint32_t child_done = 0, slot_used = 0;
+    for (int it = 0; it < ne; it++) {
+      int bc = -1, bs = -1;
+      float bestv = -INFINITY;
+      for (int c = 0; c < ne; c++) {
+        if (child_done & (1u << c)) continue;
+        float d[3];
+        for (int a = 0; a < 3; a++) d[a] = 0.5f * (lo[c][a] + hi[c][a]) - 0.5f * (nlo[a] + nhi[a]);
+        for (int sl = 0; sl < 8; sl++) {
+          if (slot_used & (1u << sl)) continue;
+          const float v = ((sl & 1) ? d[0] : -d[0]) + ((sl & 2) ? d[1] : -d[1]) + ((sl & 4) ? d[2] : -d[2]);
+          if (v > bestv) bestv = v, bc = c, bs = sl;
+        }
+      }
+      child_in_slot[bs] = bc;
+      child_done |= 1u << bc;
+      slot_used |= 1u << bs;
+    }
+    // allocation: inner children contiguous (slot order), primitive records contiguous
+    uint32_t n_inner = 0, n_prims = 0;
+    for (int k = 0; k < ne; k++) {
+      if (cnt[k] > kWideMaxLeafPrims) n_inner++; else n_prims += cnt[k];
+    }
+    const uint32_t child_base = n_inner ? atomicAdd(counters + 0, n_inner) : 0u;
+    const uint32_t prim_base = n_prims ? atomicAdd(counters + 1, n_prims) : 0u;
+    if (child_base + n_inner > node_capacity) {
+      atomicExch(counters + 2, 1u);
+      continue;
+    }
+    const uint32_t task_base = n_inner ? atomicAdd(n_out, n_inner) : 0u;
+    WideNode wn;
+    double scale[3];
+    for (int a = 0; a < 3; a++) {
+      wn.origin[a] = nlo[a];
+      const double extent = (double)nhi[a] - (double)nlo[a];
+      int e = extent > 0.0 ? (int)ceil(log2(extent / 255.0)) : -126;
+      e = max(e, -126);
+      while (ceil(extent / ldexp(1.0, e)) > 255.0) e++;
+      e = min(e, 127);
+      wn.e[a] = (uint8_t)(e + 127);
+      scale[a] = ldexp(1.0, e);
+    }
+    wn.imask = 0;
+    wn.child_base = child_base;
+    wn.prim_base = prim_base;
+    uint32_t inner_rank = 0, prim_off = 0;
+    for (int sl = 0; sl < 8; sl++) {
+      const int c = child_in_slot[sl];
+      if (c < 0) {
+        wn.meta[sl] = 0;
+        for (int a = 0; a < 3; a++) wn.qlo[a][sl] = 255, wn.qhi[a][sl] = 0;
+        continue;
+      }
+      for (int a = 0; a < 3; a++) {
+        double ql = floor(((double)lo[c][a] - (double)wn.origin[a]) / scale[a]);
+        double qh = ceil(((double)hi[c][a] - (double)wn.origin[a]) / scale[a]);
+        ql = fmin(fmax(ql, 0.0), 255.0);
+        qh = fmin(fmax(qh, 0.0), 255.0);
+        wn.qlo[a][sl] = (uint8_t)ql;
+        wn.qhi[a][sl] = (uint8_t)qh;
+      }
+      if (cnt[c] > kWideMaxLeafPrims) {
+        wn.meta[sl] = (uint8_t)((1u << 5) | (24u + (uint32_t)sl));
+        wn.imask |= (uint8_t)(1u << sl);
+        tasks_out[task_base + inner_rank] = make_uint2(child_base + inner_rank, ref[c]);
+        inner_rank++;
+      } else {
+        wn.meta[sl] = (uint8_t)((((1u << cnt[c]) - 1u) << 5) | prim_off);
+        // the <= 3 primitives of this small subtree, left to right
+        uint32_t stack[4];
+        int sp = 0;
+        stack[sp++] = ref[c];
+        uint32_t written = 0;
+        while (sp > 0) {
+          const uint32_t r = stack[--sp];
+          if (r & kLeafFlag) {
+            write_prim(s, t.vals[r & ~kLeafFlag], prims + prim_base + prim_off + written);
+            written++;
+          } else {
+            stack[sp++] = t.child_r[r];
+            stack[sp++] = t.child_l[r];
+          }
+        }
+        prim_off += cnt[c];
+      }
+    }
+    nodes[wide] = wn;
+  }
+}
+
+}  // namespace gpubvh
+}  // namespace hjk

@@ -14,6 +14,7 @@
 
 #include "../host/pass_plan.h"
 #include "../host/wide_bvh_host.h"
+#include "bvh_build_gpu.cuh"
 #include "kernels.cuh"
 
 using namespace hjk;
@@ -100,6 +101,9 @@ struct HjkContext {
   bool profiling = false;
   uint64_t wave_paths = 32u << 20;  // target camera paths per wave (4.9 GB of path state; tails amortise)
   float bvh_pad_rel = kDefaultBvhPadRel;
+  int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU LBVH builder
+  int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
+  float bvh_build_ms = 0.f;
   uint32_t fetch_threshold = kFetchThreshold, postpone_lanes = kPostponeLanes;
 
   // scene
@@ -428,6 +432,109 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   return HJK_OK;
 }
 
+
+// GPU build of the wide BVH from the scene arrays already resident on the device (bvh_build_gpu.cuh).
+// Returns HJK_OK and fills d_nodes/d_prims + meta, or HJK_ERR_UNSUPPORTED when the host builder must
+// be used instead (tiny scenes, too deep a tree, capacity overflow).
+int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_rel, WideBvh& meta) {
+  using namespace gpubvh;
+  const uint32_t n = S + Q + T;
+  if (n < 16u) return HJK_ERR_UNSUPPORTED;
+  BuildScene bs{c->d_spheres.p, c->d_quads.p, c->d_triangles.p, c->d_vertices.p, S, Q, T};
+  cudaStream_t st = c->stream;
+  const int grid = c->n_sms * 4, block = 256;
+  DevBuf<f4> blo, bhi, ilo, ihi;
+  DevBuf<uint32_t> small, vals, vals_sorted, child_l, child_r, parent_inner, parent_leaf, visits, icount;
+  DevBuf<uint64_t> keys, keys_sorted;
+  DevBuf<float> pad;
+  DevBuf<uint8_t> sort_tmp;
+  DevBuf<WideNode> tmp_nodes;
+  DevBuf<uint2> tasks_a, tasks_b;
+  HJK_CUDA(c, blo.ensure(n));
+  HJK_CUDA(c, bhi.ensure(n));
+  HJK_CUDA(c, small.ensure(16));  // [0..5] bounds, [6] bad, [8..10] counters, [12] n_in, [13] n_out
+  HJK_CUDA(c, keys.ensure(n));
+  HJK_CUDA(c, keys_sorted.ensure(n));
+  HJK_CUDA(c, vals.ensure(n));
+  HJK_CUDA(c, vals_sorted.ensure(n));
+  HJK_CUDA(c, pad.ensure(1));
+  const uint32_t init[16] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  HJK_CUDA(c, cudaMemcpyAsync(small.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+  HJK_CUDA(c, cudaEventRecord(c->ev0, st));
+  k_shape_boxes<<<grid, block, 0, st>>>(bs, n, blo.p, bhi.p, small.p, small.p + 6);
+  k_morton<<<grid, block, 0, st>>>(n, small.p, pad_rel, blo.p, bhi.p, keys.p, vals.p, pad.p);
+  size_t tmp_bytes = 0;
+  HJK_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n, 0,
+                                              63, st));
+  HJK_CUDA(c, sort_tmp.ensure(tmp_bytes));
+  HJK_CUDA(c, cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n,
+                                              0, 63, st));
+  HJK_CUDA(c, child_l.ensure(n));
+  HJK_CUDA(c, child_r.ensure(n));
+  HJK_CUDA(c, parent_inner.ensure(n));
+  HJK_CUDA(c, parent_leaf.ensure(n));
+  HJK_CUDA(c, visits.ensure(n));
+  HJK_CUDA(c, icount.ensure(n));
+  HJK_CUDA(c, ilo.ensure(n));
+  HJK_CUDA(c, ihi.ensure(n));
+  HJK_CUDA(c, cudaMemsetAsync(visits.p, 0, (size_t)n * 4, st));
+  k_radix_tree<<<grid, block, 0, st>>>((int)n, keys_sorted.p, child_l.p, child_r.p, parent_inner.p, parent_leaf.p);
+  k_fit_boxes<<<grid, block, 0, st>>>((int)n, vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, parent_inner.p,
+                                      parent_leaf.p, visits.p, ilo.p, ihi.p, icount.p);
+  HJK_CUDA(c, cudaGetLastError());
+  const uint32_t node_capacity = n;
+  HJK_CUDA(c, tmp_nodes.ensure(node_capacity));
+  HJK_CUDA(c, c->d_prims.ensure((size_t)n * HJK_PRIM_STRIDE));
+  HJK_CUDA(c, tasks_a.ensure(n));
+  HJK_CUDA(c, tasks_b.ensure(n));
+  const uint2 root_task = make_uint2(0u, 0u);
+  HJK_CUDA(c, cudaMemcpyAsync(tasks_a.p, &root_task, sizeof root_task, cudaMemcpyHostToDevice, st));
+  TreeDev tree{vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, ilo.p, ihi.p, icount.p};
+  uint2* t_in = tasks_a.p;
+  uint2* t_out = tasks_b.p;
+  uint32_t depth = 0;
+  for (;;) {
+    depth++;
+    HJK_CUDA(c, cudaMemsetAsync(small.p + 13, 0, 4, st));
+    k_collapse<<<grid, block, 0, st>>>(bs, tree, t_in, small.p + 12, t_out, small.p + 13, tmp_nodes.p,
+                                       (WidePrim*)c->d_prims.p, small.p + 8, node_capacity);
+    uint32_t n_next = 0;
+    HJK_CUDA(c, cudaMemcpyAsync(&n_next, small.p + 13, 4, cudaMemcpyDeviceToHost, st));
+    HJK_CUDA(c, cudaStreamSynchronize(st));
+    if (n_next == 0) break;
+    if (depth > (uint32_t)kMaxStack) return HJK_ERR_UNSUPPORTED;
+    HJK_CUDA(c, cudaMemcpyAsync(small.p + 12, small.p + 13, 4, cudaMemcpyDeviceToDevice, st));
+    std::swap(t_in, t_out);
+  }
+  uint32_t fin[16];
+  float pad_h = 0.f;
+  HJK_CUDA(c, cudaMemcpyAsync(fin, small.p, sizeof fin, cudaMemcpyDeviceToHost, st));
+  HJK_CUDA(c, cudaMemcpyAsync(&pad_h, pad.p, 4, cudaMemcpyDeviceToHost, st));
+  HJK_CUDA(c, cudaStreamSynchronize(st));
+  if (fin[6]) return c->fail(HJK_ERR_INVALID_ARGUMENT, "non-finite shape bounds");
+  if (fin[10] || fin[9] != n) return HJK_ERR_UNSUPPORTED;  // capacity overflow / primitive count mismatch
+  const uint32_t n_nodes = fin[8];
+  HJK_CUDA(c, c->d_nodes.ensure((size_t)n_nodes * 5));
+  HJK_CUDA(c, cudaMemcpyAsync(c->d_nodes.p, tmp_nodes.p, (size_t)n_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+  HJK_CUDA(c, cudaEventRecord(c->ev1, st));
+  HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+  cudaEventElapsedTime(&c->bvh_build_ms, c->ev0, c->ev1);
+  meta.depth = depth;
+  meta.n_shapes = n;
+  meta.pad = pad_h;
+  meta.nodes.clear();
+  meta.prims.clear();
+  c->n_nodes = n_nodes;
+  c->n_prims = n;
+  if (c->bvh_validate) {
+    meta.nodes.resize(n_nodes);
+    meta.prims.resize(n);
+    HJK_CUDA(c, cudaMemcpy(meta.nodes.data(), c->d_nodes.p, (size_t)n_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    HJK_CUDA(c, cudaMemcpy(meta.prims.data(), c->d_prims.p, (size_t)n * sizeof(WidePrim), cudaMemcpyDeviceToHost));
+  }
+  return HJK_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -551,16 +658,7 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
     if (e.shape >= n_shapes || (mats[e.shape] >> HJK_MATERIAL_TAG_SHIFT) != HJK_MAT_EMISSIVE)
       return c->fail(HJK_ERR_INVALID_ARGUMENT, "emitter %llu does not point at an emissive shape", (unsigned long long)i);
   }
-  WideBvh bvh;
-  std::string err;
-  if (!build_wide_bvh(*s, c->bvh_pad_rel, bvh, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
-  if (bvh.depth > (uint32_t)kMaxStack)
-    return c->fail(HJK_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", bvh.depth, kMaxStack);
-
   int rc;
-  HjkArray a_nodes{bvh.nodes.data(), bvh.nodes.size()}, a_prims{bvh.prims.data(), bvh.prims.size()};
-  if ((rc = upload(c, c->d_nodes, a_nodes, sizeof(WideNode)))) return rc;
-  if ((rc = upload(c, c->d_prims, a_prims, sizeof(WidePrim)))) return rc;
   if ((rc = upload(c, c->d_spheres, s->spheres, 16))) return rc;
   if ((rc = upload(c, c->d_quads, s->quads, 48))) return rc;
   if ((rc = upload(c, c->d_triangles, s->triangles, 12))) return rc;
@@ -571,6 +669,38 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   if ((rc = upload(c, c->d_diffusecb, s->diffusecb, 32))) return rc;
   if ((rc = upload(c, c->d_dielectric, s->dielectric, 16))) return rc;
   if ((rc = upload(c, c->d_emissive, s->emissive, 16))) return rc;
+  if (s->triangles.count) {
+    const uint32_t* tri = (const uint32_t*)s->triangles.ptr;
+    for (uint64_t i = 0; i < 3 * s->triangles.count; i++)
+      if (tri[i] >= s->vertices.count) return c->fail(HJK_ERR_INVALID_ARGUMENT, "triangle vertex index out of range");
+  }
+  WideBvh bvh;
+  std::string err;
+  bool built_on_gpu = false;
+  c->bvh_build_ms = 0.f;
+  if (c->bvh_builder == 1) {
+    rc = build_bvh_gpu(c, info->num_spheres, info->num_quads, info->num_triangles, c->bvh_pad_rel, bvh);
+    if (rc == HJK_OK) {
+      built_on_gpu = true;
+      sphere_guard_bounds(*s, bvh);
+      if (c->bvh_validate && !validate_wide_bvh(*s, bvh, err))
+        return c->fail(HJK_ERR_CUDA, "GPU-built BVH failed the structural check: %s", err.c_str());
+      bvh.nodes.clear();
+      bvh.prims.clear();
+    } else if (rc != HJK_ERR_UNSUPPORTED) {
+      return rc;
+    }
+  }
+  if (!built_on_gpu) {
+    if (!build_wide_bvh(*s, c->bvh_pad_rel, bvh, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+    if (bvh.depth > (uint32_t)kMaxStack)
+      return c->fail(HJK_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", bvh.depth, kMaxStack);
+    HjkArray a_nodes{bvh.nodes.data(), bvh.nodes.size()}, a_prims{bvh.prims.data(), bvh.prims.size()};
+    if ((rc = upload(c, c->d_nodes, a_nodes, sizeof(WideNode)))) return rc;
+    if ((rc = upload(c, c->d_prims, a_prims, sizeof(WidePrim)))) return rc;
+    c->n_nodes = bvh.nodes.size();
+    c->n_prims = bvh.prims.size();
+  }
   HJK_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
 
   SceneDev& d = c->scene;
@@ -585,8 +715,6 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   for (int k = 0; k < 4; k++) d.sph_centre[k] = bvh.sph_centre[k];
   d.sph_rmin = bvh.sph_rmin, d.sph_rmax = bvh.sph_rmax;
   c->has_extinction = has_ext;
-  c->n_nodes = bvh.nodes.size();
-  c->n_prims = bvh.prims.size();
   bvh.nodes.clear();
   bvh.nodes.shrink_to_fit();
   bvh.prims.clear();
@@ -914,6 +1042,11 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "bvh_pad_rel_e9") {  // relative primitive-box pad in units of 1e-9 (next scene upload)
     if (value < 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "pad must be non-negative");
     c->bvh_pad_rel = (float)value * 1e-9f;
+  } else if (k == "bvh_builder") {  // 0 host SAH (default), 1 GPU LBVH; takes effect at the next scene upload
+    if (value < 0 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->bvh_builder = (int)value;
+  } else if (k == "bvh_validate") {
+    c->bvh_validate = value != 0;
   } else if (k == "fetch_threshold") {
     if (value < 0 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->fetch_threshold = (uint32_t)value;
@@ -944,6 +1077,8 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "blocks_per_sm_tile") *out = c->blocks_tile;
   else if (k == "wave_paths") *out = (int64_t)c->wave_paths;
   else if (k == "has_extinction") *out = c->has_extinction ? 1 : 0;
+  else if (k == "bvh_builder") *out = c->bvh_builder;
+  else if (k == "bvh_build_us") *out = (int64_t)(c->bvh_build_ms * 1000.f);
   else if (k == "unresolved_ties") *out = (int64_t)c->unresolved_last;
   else if (k == "device") *out = c->device;
   else if (k == "width") *out = c->width;

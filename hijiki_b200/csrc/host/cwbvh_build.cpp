@@ -366,6 +366,32 @@ Box shape_box(const HjkScene& s, uint32_t shape) {
 
 }  // namespace
 
+// bounding ball of the sphere centres + radius range: inputs of the traversal's sphere guard
+void sphere_guard_bounds(const HjkScene& s, WideBvh& out) {
+  const uint64_t S = s.spheres.count;
+  for (int k = 0; k < 4; k++) out.sph_centre[k] = 0.f;
+  out.sph_rmin = out.sph_rmax = 0.f;
+  if (!S) return;
+  const HjkSphere* sp = (const HjkSphere*)s.spheres.ptr;
+  Box cb;
+  cb.reset();
+  float rmin = kInf, rmax = 0.f;
+  for (uint64_t i = 0; i < S; i++) {
+    cb.grow(sp[i].position);
+    rmin = std::min(rmin, std::fabs(sp[i].radius));
+    rmax = std::max(rmax, std::fabs(sp[i].radius));
+  }
+  float rad2 = 0.f;
+  for (int k = 0; k < 3; k++) {
+    out.sph_centre[k] = 0.5f * (cb.lo[k] + cb.hi[k]);
+    const float h = 0.5f * (cb.hi[k] - cb.lo[k]);
+    rad2 += h * h;
+  }
+  out.sph_centre[3] = std::sqrt(rad2) * 1.0001f;
+  out.sph_rmin = rmin;
+  out.sph_rmax = rmax;
+}
+
 bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string& err) {
   out = WideBvh();
   const uint64_t S = s.spheres.count, Q = s.quads.count, T = s.triangles.count;
@@ -556,26 +582,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
   }
   lap("emit wide nodes");
   out.n_shapes = n;
-  if (S) {
-    const HjkSphere* sp = (const HjkSphere*)s.spheres.ptr;
-    Box cb;
-    cb.reset();
-    float rmin = kInf, rmax = 0.f;
-    for (uint64_t i = 0; i < S; i++) {
-      cb.grow(sp[i].position);
-      rmin = std::min(rmin, std::fabs(sp[i].radius));
-      rmax = std::max(rmax, std::fabs(sp[i].radius));
-    }
-    float rad2 = 0.f;
-    for (int k = 0; k < 3; k++) {
-      out.sph_centre[k] = 0.5f * (cb.lo[k] + cb.hi[k]);
-      const float h = 0.5f * (cb.hi[k] - cb.lo[k]);
-      rad2 += h * h;
-    }
-    out.sph_centre[3] = std::sqrt(rad2) * 1.0001f;
-    out.sph_rmin = rmin;
-    out.sph_rmax = rmax;
-  }
+  sphere_guard_bounds(s, out);
   return true;
 }
 

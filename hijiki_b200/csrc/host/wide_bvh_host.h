@@ -26,5 +26,6 @@ constexpr float kDefaultBvhPadRel = 1e-5f;
 
 bool build_wide_bvh(const HjkScene& scene, float pad_rel, WideBvh& out, std::string& err);
 bool validate_wide_bvh(const HjkScene& scene, const WideBvh& bvh, std::string& err);
+void sphere_guard_bounds(const HjkScene& scene, WideBvh& out);
 
 }  // namespace hjk
