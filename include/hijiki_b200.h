@@ -301,6 +301,17 @@ HJK_API int hjk_set_stream(HjkContext* ctx, void* cuda_stream);
 
 /* ----------------------------------------------------- misc / profiling */
 HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-event timing */
+/* Tuning options (all have measured defaults; none changes results):
+ *   "wave_paths"             camera paths rendered per wave (default 32 Mi)
+ *   "bvh_builder"            0 = host SAH builder (default), 1 = GPU LBVH builder; next hjk_scene_upload
+ *   "bvh_validate"           1 = run the host structural check on a GPU-built tree
+ *   "bvh_pad_rel_e9"         outward pad of primitive boxes, in 1e-9 of the scene extent (default 10000)
+ *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default 20)
+ *   "postpone_lanes"         postpone primitive tests that fewer lanes than this would run (default 8)
+ *   "blocks_per_sm_traverse", "blocks_per_sm_tile"   persistent-grid sizes
+ * Info keys: "n_sms", "bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "bvh_builder", "bvh_build_us",
+ *   "wave_paths", "has_extinction", "unresolved_ties", "width", "height", "device",
+ *   "blocks_per_sm_traverse", "blocks_per_sm_tile". */
 HJK_API int hjk_set_option(HjkContext* ctx, const char* key, int64_t value);
 HJK_API int hjk_get_info(HjkContext* ctx, const char* key, int64_t* out_value);
 HJK_API const char* hjk_version(void);
