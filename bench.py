@@ -363,6 +363,25 @@ def main():
         e2e_ms = e0.elapsed_time(e1)
         result_mean = float(out_host[..., :3].mean())
 
+    # the path's one collective, timed alone: all-reduce(sum) of the W x H float4 accumulator
+    allreduce_info = None
+    if world > 1:
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        allreduce()
+        a0.record(stream)
+        for _ in range(reps):
+            allreduce()
+        a1.record(stream)
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / reps
+        nbytes = width * height * 16
+        allreduce_info = {"bytes": nbytes, "ms": ar_ms,
+                          "bus_gbs": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                          "note": "torch.distributed NCCL on the render stream; bus bandwidth = 2(N-1)/N * S / t "
+                                  "(nominal NVLink 5: 900 GB/s per direction)"}
+
     info = {k: ctx.get_info(k) for k in ("bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "wave_paths",
                                           "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_sms")}
     ctx.close()
@@ -442,6 +461,8 @@ def main():
             line["e2e"] = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                            "h2d_bytes_per_step": int(slices[0].nbytes), "d2h_bytes_per_step": width * height * 16,
                            "ms_per_step": e2e_ms / args.steps}
+        if allreduce_info:
+            line["allreduce"] = allreduce_info
         if denoiser:
             denoiser["peak"] = peak
             denoiser["frac"] = denoiser["achieved"] / peak
