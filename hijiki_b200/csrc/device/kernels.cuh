@@ -28,10 +28,8 @@ namespace hjk {
 // per-bounce device counters (uint32 each)
 enum : uint32_t {
   CTR_EXT = 0,      // extension rays entering this bounce
-  CTR_TAG0 = 1,     // .. CTR_TAG0+4: hits per material tag after extend
   CTR_SHADOW = 6,   // shadow rays emitted by this bounce
-  CTR_EXT_CURSOR = 7,
-  CTR_SH_CURSOR = 8,
+  CTR_EXT_CURSOR = 7,  // work cursor of k_trace(bounce): shadow rays of bounce-1, then extension rays
   CTR_STRIDE = 16
 };
 

@@ -198,10 +198,11 @@ enum {
   HJK_K_RAYGEN = 0,
   HJK_K_EXTEND = 1,
   HJK_K_SHADE = 2,
-  HJK_K_SHADOW = 3,
+  HJK_K_SHADOW = 3, /* unused since shadow rays are traced by the same launches as extension rays
+                       (their time is in HJK_K_EXTEND) */
   HJK_K_RECON = 4,
   HJK_K_OTHER = 5,
-  HJK_K_SORT = 6 /* material binning / queue compaction */
+  HJK_K_SORT = 6 /* unused since the material sort is tile-local inside the shade kernel */
 };
 
 typedef struct HjkStats {
