@@ -304,3 +304,41 @@ def quad_room_scene():
                        materials=materials, diffuse=[(0.7, 0.7, 0.7, 0), (0.7, 0.2, 0.2, 0), (0.2, 0.6, 0.25, 0)],
                        diffusecb=[(0.8, 0.8, 0.8, 0.25, 0.15, 0.15, 0.3, 0.25)],
                        dielectric=[(0.9, 0.3, 0.2, 1.5)], emissive=[(12, 12, 12, 0)])
+
+
+def random_scene(seed: int, n_tris: int = 60, n_spheres: int = 3, n_quads: int = 2):
+    """A random soup in the binding layouts: triangles with random normals/uvs, spheres, quads, every
+    material tag (tinted glass included), at least one emitter of each emissive-capable shape kind."""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    D, CB, MI, DI, EM = _abi.MAT_DIFFUSE, _abi.MAT_DIFFUSECBOARD, _abi.MAT_MIRROR, _abi.MAT_DIELECTRIC, _abi.MAT_EMISSIVE
+    verts = np.zeros((3 * n_tris, 8), f32)
+    centres = rng.uniform(-1.5, 1.5, (n_tris, 1, 3))
+    verts[:, :3] = (centres + rng.normal(0, 0.5, (n_tris, 3, 3))).reshape(-1, 3)
+    nrm = rng.normal(0, 1, (3 * n_tris, 3))
+    verts[:, 4:7] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    verts[:, 3] = rng.uniform(0, 4, 3 * n_tris)
+    verts[:, 7] = rng.uniform(0, 4, 3 * n_tris)
+    tris = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+    spheres = np.concatenate([rng.uniform(-1.5, 1.5, (n_spheres, 3)), rng.uniform(0.2, 0.5, (n_spheres, 1))], 1)
+    quads = []
+    for _ in range(n_quads):
+        o = rng.uniform(-2, 2, 3)
+        e1 = rng.normal(0, 1, 3)
+        e2 = np.cross(e1, rng.normal(0, 1, 3))
+        quads.append([*o, 0, *e1, 0, *(e2 / np.linalg.norm(e2) * rng.uniform(0.5, 1.5)), 0])
+    n_shapes = n_spheres + n_quads + n_tris
+    diffuse = np.concatenate([rng.uniform(0.2, 0.9, (4, 3)), np.zeros((4, 1))], 1)
+    diffusecb = np.array([[0.8, 0.8, 0.7, 0.3, 0.2, 0.3, 0.2, 0.4], [0.6, 0.1, 0.1, 0.15, 0.9, 0.9, 0.9, 0.2]])
+    dielectric = np.array([[0, 0, 0, 1.5], [0.6, 0.2, 0.9, 1.33]])
+    emissive = np.array([[8, 8, 8, 0], [4, 6, 9, 0]])
+    choices = [(D, 0), (D, 1), (D, 2), (D, 3), (CB, 0), (CB, 1), (MI, 0), (DI, 0), (DI, 1), (EM, 0), (EM, 1)]
+    weights = np.array([3, 3, 3, 3, 2, 2, 2, 2, 2, 1, 1], float)
+    mats = [choices[k] for k in rng.choice(len(choices), n_shapes, p=weights / weights.sum())]
+    mats[0] = (EM, 0)                       # an emissive sphere
+    mats[n_spheres] = (EM, 1)               # an emissive quad
+    mats[n_spheres + n_quads] = (EM, 0)     # an emissive triangle
+    half = rng.uniform(-0.3, 0.3)
+    camera = ((0.0, 0.0, 6.0), (float(np.sin(half)), 0.0, 0.0, float(np.cos(half))), 45.0)
+    return CustomScene(camera, spheres=spheres, quads=quads, triangles=tris, vertices=verts, materials=mats,
+                       diffuse=diffuse, diffusecb=diffusecb, dielectric=dielectric, emissive=emissive)
