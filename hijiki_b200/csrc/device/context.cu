@@ -101,6 +101,9 @@ struct HjkContext {
   bool profiling = false;
   uint64_t wave_paths = 32u << 20;  // target camera paths per wave (4.9 GB of path state; tails amortise)
   float bvh_pad_rel = kDefaultBvhPadRel;
+  int coop_trace = 1;    // 1 = k_trace_coop: pooled primitive tests (default mode only); 0 = per-lane k_trace
+  uint32_t coop_batch_cost = 180;
+  int blocks_coop[2] = {0, 0};
   int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU LBVH builder
   int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
   float bvh_build_ms = 0.f;
@@ -336,6 +339,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.has_extinction = c->has_extinction ? 1u : 0u;
   w.fetch_threshold = c->fetch_threshold, w.postpone_lanes = c->postpone_lanes;
   w.unresolved = c->d_unresolved.p;
+  w.coop_batch_cost = c->coop_batch_cost;
   const bool exact = (prm->flags & HJK_RENDER_EXACT_TIES) != 0;
   const bool guard = c->scene.num_spheres != 0;
   const int g_trav = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_trav_v[guard][exact]);
@@ -364,7 +368,13 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     for (uint32_t b = 0;; b++) {
       {
         KernelTimer t(c, stats, HJK_K_EXTEND);
-        if (guard && exact)
+        if (c->coop_trace && !exact) {
+          const int g_coop = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_coop[guard]);
+          if (guard)
+            k_trace_coop<true><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+          else
+            k_trace_coop<false><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+        } else if (guard && exact)
           k_trace<true, true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
         else if (guard)
           k_trace<true, false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
@@ -589,6 +599,10 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, kTravThreads, 0);
   c->blocks_trav_v[1][1] = std::max(occ, 1);
   c->blocks_trav = c->blocks_trav_v[0][0];
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<false>, kTravThreads, 0);
+  c->blocks_coop[0] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<true>, kTravThreads, 0);
+  c->blocks_coop[1] = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
   c->blocks_tile = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
@@ -1042,6 +1056,11 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "bvh_pad_rel_e9") {  // relative primitive-box pad in units of 1e-9 (next scene upload)
     if (value < 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "pad must be non-negative");
     c->bvh_pad_rel = (float)value * 1e-9f;
+  } else if (k == "coop_trace") {
+    c->coop_trace = value != 0;
+  } else if (k == "coop_batch_cost") {
+    if (value < 0 || value > 100000) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->coop_batch_cost = (uint32_t)value;
   } else if (k == "bvh_builder") {  // 0 host SAH (default), 1 GPU LBVH; takes effect at the next scene upload
     if (value < 0 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->bvh_builder = (int)value;

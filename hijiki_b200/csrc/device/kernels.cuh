@@ -63,6 +63,7 @@ struct WaveDev {
   uint32_t has_extinction;
   uint32_t fetch_threshold;      // refill a warp when fewer lanes than this are busy
   uint32_t postpone_lanes;       // postpone primitive tests that fewer lanes than this would run
+  uint32_t coop_batch_cost;      // pooled primitive tests: assumed instructions per batch of 32 (0 = always pool)
   uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
 };
 
@@ -287,6 +288,175 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
   }
 }
 
+// Warp-cooperative variant.  Node steps stay per lane (one ray per lane, 26 of 32 lanes busy), but
+// the primitive tests of a step are pooled: the pending (ray, primitive) pairs of all 32 lanes are
+// numbered with a warp prefix sum and tested 32 at a time, one pair per lane, by whichever lane is
+// free — the owner's ray travels by shuffle, the nearest accepted hit comes back through a 64-bit
+// shared-memory atomicMin keyed by (t, testing lane).  In the per-lane loop the same tests ran at ~9
+// of 32 lanes (lanes of one warp reach leaves holding 0..24 primitives at the same step).
+// Closest hit = the candidate of smallest t under the ray's current interval, then tMax = t - M_EPS:
+// the same result as the sequential rule except inside clusters closer than M_EPS (ties).  The
+// exact-tie mode keeps the per-lane loop (it must record every candidate).
+template <bool GUARD, class IO>
+__device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO& io, uint32_t n, uint32_t* cursor,
+                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost) {
+  __shared__ uint2 sm_stack[kSmStack * kTravThreads];
+  __shared__ unsigned long long sm_best[kTravThreads];
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t FULL = 0xFFFFFFFFu;
+  DevStack st;
+  st.sm = sm_stack + threadIdx.x;
+  st.n = 0;
+  TravState s;
+  s.tg_y = 0, s.ng_y = 0;
+  bool active = false, exhausted = false;
+  for (;;) {
+    // ---- refill
+    const uint32_t busy = __ballot_sync(FULL, active);
+    if (!exhausted && __popc(busy) < fetch_threshold) {
+      const uint32_t need = ~busy;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(need));
+      base = __shfl_sync(FULL, base, 0);
+      if (!active) {
+        const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
+        if (i < n) {
+          io.template load<GUARD>(i, s);
+          st.n = 0;
+          active = true;
+        }
+      }
+      if (base + __popc(need) >= n) exhausted = true;
+    }
+    if (__ballot_sync(FULL, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- node step (per lane)
+    if (active) {
+      if (s.ng_y > 0x00FFFFFFu) {
+        const uint32_t hits_imask = s.ng_y;
+        const int bit = hi_bit(hits_imask);
+        s.ng_y &= ~(1u << bit);
+        if (s.ng_y > 0x00FFFFFFu) st.push(s.ng_x, s.ng_y);
+        const uint32_t slot = ((uint32_t)bit - 24u) ^ (s.octinv4 & 0xFFu);
+        const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xFFFFFFFFu << slot));
+        const f4* np = sc.nodes + (size_t)(s.ng_x + rel) * 5;
+        const f4 q0 = ld16(np), q1 = ld16(np + 1), q2 = ld16(np + 2), q3 = ld16(np + 3), q4 = ld16(np + 4);
+        const uint32_t hitmask = intersect_node<GUARD, false>(sc, s, q0, q1, q2, q3, q4);
+        s.ng_x = __float_as_uint(q1.x);
+        s.ng_y = (hitmask & 0xFF000000u) | (__float_as_uint(q0.w) >> 24);
+        s.tg_x = __float_as_uint(q1.y);
+        s.tg_y = hitmask & 0x00FFFFFFu;
+      } else {
+        s.tg_y = 0;
+      }
+    }
+    // ---- primitive tests: pooled over the warp when the per-lane counts are skewed enough to pay for
+    // the pooling overhead (~70 instructions per batch of 32), else each lane tests its own
+    const uint32_t cnt = active ? (uint32_t)__popc(s.tg_y) : 0u;
+    const uint32_t sum_cnt = __reduce_add_sync(FULL, cnt), max_cnt = __reduce_max_sync(FULL, cnt);
+    if (max_cnt * 71u <= ((sum_cnt + 31u) >> 5) * coop_batch_cost) {
+      while (s.tg_y) {
+        const int i = hi_bit(s.tg_y);
+        s.tg_y &= ~(1u << i);
+        const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * HJK_PRIM_STRIDE;
+        const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
+#if HJK_PRIM_STRIDE == 4
+        const f4 r3 = ld16(pp + 3);
+#else
+        const f4 r3 = r2;
+#endif
+        float t, u, v;
+        if (intersect_prim(sc, s, r0, r1, r2, r3, t, u, v)) {
+          s.hit_id = (int32_t)__float_as_uint(r0.w);
+          s.hit_t = t, s.hit_u = u, s.hit_v = v;
+          if (s.slot >> 31) break;
+          s.tmax = x::sub(t, eps);  // scene.glsl:116
+        }
+      }
+      s.tg_y = 0;
+    }
+    const uint32_t pooled = (active && s.tg_y) ? cnt : 0u;
+    uint32_t incl = pooled;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(FULL, incl, o);
+      if ((int)lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const uint32_t excl = incl - pooled;
+    unsigned long long cur_key = ~0ull;
+    if (total) sm_best[threadIdx.x] = ~0ull;
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32u) {
+      const uint32_t j = base + lane;
+      const uint32_t jj = j < total ? j : total - 1u;
+      // owner = first lane whose inclusive count exceeds jj
+      uint32_t owner = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t v = __shfl_sync(FULL, incl, (int)(owner + step - 1u));
+        if (v <= jj) owner += step;
+      }
+      const uint32_t o_excl = __shfl_sync(FULL, excl, (int)owner);
+      uint32_t bits = __shfl_sync(FULL, s.tg_y, (int)owner);
+      const uint32_t o_tgx = __shfl_sync(FULL, s.tg_x, (int)owner);
+      TravState r;
+      r.ox = __shfl_sync(FULL, s.ox, (int)owner), r.oy = __shfl_sync(FULL, s.oy, (int)owner);
+      r.oz = __shfl_sync(FULL, s.oz, (int)owner), r.dx = __shfl_sync(FULL, s.dx, (int)owner);
+      r.dy = __shfl_sync(FULL, s.dy, (int)owner), r.dz = __shfl_sync(FULL, s.dz, (int)owner);
+      r.tmin = __shfl_sync(FULL, s.tmin, (int)owner), r.tmax = __shfl_sync(FULL, s.tmax, (int)owner);
+      float t = 0.f, u = 0.f, v = 0.f;
+      uint32_t id = 0;
+      if (j < total) {
+        for (uint32_t k = jj - o_excl; k > 0; k--) bits &= bits - 1u;  // k-th pending primitive of the owner
+        const uint32_t prim_index = o_tgx + (uint32_t)(__ffs((int)bits) - 1);
+        const f4* pp = sc.prims + (size_t)prim_index * HJK_PRIM_STRIDE;
+        const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
+#if HJK_PRIM_STRIDE == 4
+        const f4 r3 = ld16(pp + 3);
+#else
+        const f4 r3 = r2;
+#endif
+        if (intersect_prim(sc, r, r0, r1, r2, r3, t, u, v)) {
+          id = __float_as_uint(r0.w);
+          const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | lane;
+          atomicMin(&sm_best[(threadIdx.x & ~31u) + owner], key);
+        }
+      }
+      __syncwarp();
+      // owners pick up an improvement made by this batch; the winner's u, v, id come by shuffle
+      unsigned long long key = cur_key;
+      if (pooled) key = sm_best[threadIdx.x];
+      const bool improved = key < cur_key;
+      const int src = improved ? (int)(key & 31ull) : (int)lane;
+      const float wu = __shfl_sync(FULL, u, src), wv = __shfl_sync(FULL, v, src);
+      const uint32_t wid = __shfl_sync(FULL, id, src);
+      if (improved) {
+        cur_key = key;
+        s.hit_id = (int32_t)wid;
+        s.hit_t = __uint_as_float((uint32_t)(key >> 32));
+        s.hit_u = wu, s.hit_v = wv;
+        s.tmax = x::sub(s.hit_t, eps);  // scene.glsl:116
+      }
+      __syncwarp();
+    }
+    // ---- advance / finish (per lane)
+    if (active) {
+      s.tg_y = 0;
+      bool done = (s.slot >> 31) && s.hit_id >= 0;  // any-hit ray: first accepted primitive ends it
+      if (!done && s.ng_y <= 0x00FFFFFFu) {
+        if (st.empty()) done = true; else st.pop(s.ng_x, s.ng_y);
+      }
+      if (done) {
+        io.store(s);
+        active = false;
+      }
+    }
+  }
+}
+
 // GUARD: the scene contains spheres (sphere guard of traverse.cuh compiled in).
 // bounce in [0, max_bounces]: extension rays of `bounce` (none at max_bounces) + shadow rays of bounce-1.
 // Without the sphere guard the kernel fits 56 registers (9 CTAs = 36 warps per SM, measured best of
@@ -300,6 +470,16 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS
   const WaveIO io{w, w.ext_q[bounce & 1u], n_shadow};
   traverse_queue<GUARD, EXACT>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
                                (int)w.postpone_lanes, w.unresolved);
+}
+// same work, pooled primitive tests (traverse_queue_coop)
+template <bool GUARD>
+__global__ void __launch_bounds__(kTravThreads, 8) k_trace_coop(WaveDev w, uint32_t bounce, uint32_t last) {
+  uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
+  const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
+  const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
+  const WaveIO io{w, w.ext_q[bounce & 1u], n_shadow};
+  traverse_queue_coop<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
+                             w.coop_batch_cost);
 }
 // cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode)
 template <bool GUARD, bool EXACT>

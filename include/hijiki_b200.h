@@ -308,7 +308,11 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *   "bvh_validate"           1 = run the host structural check on a GPU-built tree
  *   "bvh_pad_rel_e9"         outward pad of primitive boxes, in 1e-9 of the scene extent (default 10000)
  *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default 20)
- *   "postpone_lanes"         postpone primitive tests that fewer lanes than this would run (default 8)
+ *   "coop_trace"             1 = k_trace_coop (default): a warp pools the primitive tests of its leaves and
+ *                            spreads them over all 32 lanes when that is cheaper; 0 = per-lane k_trace
+ *   "coop_batch_cost"        assumed instructions per pooled batch of 32 tests (default 180; 0 = always pool)
+ *   "postpone_lanes"         per-lane k_trace: postpone primitive tests that fewer lanes than this would run
+ *                            (default 8)
  *   "blocks_per_sm_traverse", "blocks_per_sm_tile"   persistent-grid sizes
  * Info keys: "n_sms", "bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "bvh_builder", "bvh_build_us",
  *   "wave_paths", "has_extinction", "unresolved_ties", "width", "height", "device",

@@ -400,3 +400,31 @@ def test_gpu_built_bvh_gives_the_same_hits(gpu_ctx, kind, mode):
     finally:
         gpu_ctx.set_option("bvh_builder", 0)
         gpu_ctx.set_option("bvh_validate", 0)
+
+
+@pytest.mark.parametrize("coop,batch_cost", [(1, 180), (1, 0), (0, 180)])
+@pytest.mark.parametrize("kind,max_bounces,use_bvh", [("cbox", 8, 0), ("cbox_spheres", 1000, 0), ("spheres", 16, 2)])
+def test_trace_kernel_variants_match_oracle(gpu_ctx, kind, max_bounces, use_bvh, coop, batch_cost):
+    """The default-mode trace kernel comes in two forms: k_trace_coop (default; a warp pools its
+    primitive tests and spreads them over all 32 lanes when that is cheaper, batch_cost 0 = always)
+    and the per-lane k_trace (coop_trace=0).  Same hits off ties, same frames within the tie budget."""
+    compiled = _compiled(kind)
+    gpu_ctx.scene_upload(compiled)
+    gpu_ctx.set_option("coop_trace", coop)
+    gpu_ctx.set_option("coop_batch_cost", batch_cost)
+    try:
+        w, h, bs, spp = 136, 100, 64, 3
+        blocks = hj.ImageBlockGenerator(w, h, bs, spp).blocks()
+        gpu_ctx.frame_begin(w, h)
+        st = gpu_ctx.render(blocks, hj.make_params(max_bounces=max_bounces))
+        acc_g = gpu_ctx.readback(normalise=False)
+    finally:
+        gpu_ctx.set_option("coop_trace", 1)
+        gpu_ctx.set_option("coop_batch_cost", 180)
+    acc_o, ost = _oracle_render(compiled, blocks, max_bounces, bs, use_bvh)
+    diff = (acc_o.view(np.uint32) != acc_g.view(np.uint32)).any(axis=2)
+    print(f"coop={coop}/{batch_cost} {kind}: texels differing {int(diff.sum())}; rays {st.n_extension_rays}+{st.n_shadow_rays} vs "
+          f"{ost.n_extension_rays}+{ost.n_shadow_rays}")
+    assert st.n_paths == ost.n_paths
+    assert diff.sum() <= 25 * 4
+    assert abs(st.n_extension_rays - ost.n_extension_rays) <= 100
