@@ -375,72 +375,72 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
           s.tmax = x::sub(t, eps);  // scene.glsl:116
         }
       }
-      s.tg_y = 0;
-    }
-    const uint32_t pooled = (active && s.tg_y) ? cnt : 0u;
-    uint32_t incl = pooled;
+    } else {
+      const uint32_t pooled = cnt;
+      uint32_t incl = pooled;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(FULL, incl, o);
-      if ((int)lane >= o) incl += v;
-    }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    const uint32_t excl = incl - pooled;
-    unsigned long long cur_key = ~0ull;
-    if (total) sm_best[threadIdx.x] = ~0ull;
-    __syncwarp();
-    for (uint32_t base = 0; base < total; base += 32u) {
-      const uint32_t j = base + lane;
-      const uint32_t jj = j < total ? j : total - 1u;
-      // owner = first lane whose inclusive count exceeds jj
-      uint32_t owner = 0;
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        const uint32_t v = __shfl_sync(FULL, incl, (int)(owner + step - 1u));
-        if (v <= jj) owner += step;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if ((int)lane >= o) incl += v;
       }
-      const uint32_t o_excl = __shfl_sync(FULL, excl, (int)owner);
-      uint32_t bits = __shfl_sync(FULL, s.tg_y, (int)owner);
-      const uint32_t o_tgx = __shfl_sync(FULL, s.tg_x, (int)owner);
-      TravState r;
-      r.ox = __shfl_sync(FULL, s.ox, (int)owner), r.oy = __shfl_sync(FULL, s.oy, (int)owner);
-      r.oz = __shfl_sync(FULL, s.oz, (int)owner), r.dx = __shfl_sync(FULL, s.dx, (int)owner);
-      r.dy = __shfl_sync(FULL, s.dy, (int)owner), r.dz = __shfl_sync(FULL, s.dz, (int)owner);
-      r.tmin = __shfl_sync(FULL, s.tmin, (int)owner), r.tmax = __shfl_sync(FULL, s.tmax, (int)owner);
-      float t = 0.f, u = 0.f, v = 0.f;
-      uint32_t id = 0;
-      if (j < total) {
-        for (uint32_t k = jj - o_excl; k > 0; k--) bits &= bits - 1u;  // k-th pending primitive of the owner
-        const uint32_t prim_index = o_tgx + (uint32_t)(__ffs((int)bits) - 1);
-        const f4* pp = sc.prims + (size_t)prim_index * HJK_PRIM_STRIDE;
-        const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
-#if HJK_PRIM_STRIDE == 4
-        const f4 r3 = ld16(pp + 3);
-#else
-        const f4 r3 = r2;
-#endif
-        if (intersect_prim(sc, r, r0, r1, r2, r3, t, u, v)) {
-          id = __float_as_uint(r0.w);
-          const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | lane;
-          atomicMin(&sm_best[(threadIdx.x & ~31u) + owner], key);
+      const uint32_t total = sum_cnt;
+      const uint32_t excl = incl - pooled;
+      unsigned long long cur_key = ~0ull;
+      sm_best[threadIdx.x] = ~0ull;
+      __syncwarp();
+      for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t j = base + lane;
+        const uint32_t jj = j < total ? j : total - 1u;
+        // owner = first lane whose inclusive count exceeds jj
+        uint32_t owner = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const uint32_t v = __shfl_sync(FULL, incl, (int)(owner + step - 1u));
+          if (v <= jj) owner += step;
         }
+        const uint32_t o_excl = __shfl_sync(FULL, excl, (int)owner);
+        uint32_t bits = __shfl_sync(FULL, s.tg_y, (int)owner);
+        const uint32_t o_tgx = __shfl_sync(FULL, s.tg_x, (int)owner);
+        TravState r;
+        r.ox = __shfl_sync(FULL, s.ox, (int)owner), r.oy = __shfl_sync(FULL, s.oy, (int)owner);
+        r.oz = __shfl_sync(FULL, s.oz, (int)owner), r.dx = __shfl_sync(FULL, s.dx, (int)owner);
+        r.dy = __shfl_sync(FULL, s.dy, (int)owner), r.dz = __shfl_sync(FULL, s.dz, (int)owner);
+        r.tmin = __shfl_sync(FULL, s.tmin, (int)owner), r.tmax = __shfl_sync(FULL, s.tmax, (int)owner);
+        float t = 0.f, u = 0.f, v = 0.f;
+        uint32_t id = 0;
+        if (j < total) {
+          for (uint32_t k = jj - o_excl; k > 0; k--) bits &= bits - 1u;  // k-th pending primitive of the owner
+          const uint32_t prim_index = o_tgx + (uint32_t)(__ffs((int)bits) - 1);
+          const f4* pp = sc.prims + (size_t)prim_index * HJK_PRIM_STRIDE;
+          const f4 r0 = ld16(pp), r1 = ld16(pp + 1), r2 = ld16(pp + 2);
+#if HJK_PRIM_STRIDE == 4
+          const f4 r3 = ld16(pp + 3);
+#else
+          const f4 r3 = r2;
+#endif
+          if (intersect_prim(sc, r, r0, r1, r2, r3, t, u, v)) {
+            id = __float_as_uint(r0.w);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | lane;
+            atomicMin(&sm_best[(threadIdx.x & ~31u) + owner], key);
+          }
+        }
+        __syncwarp();
+        // owners pick up an improvement made by this batch; the winner's u, v, id come by shuffle
+        unsigned long long key = cur_key;
+        if (pooled) key = sm_best[threadIdx.x];
+        const bool improved = key < cur_key;
+        const int src = improved ? (int)(key & 31ull) : (int)lane;
+        const float wu = __shfl_sync(FULL, u, src), wv = __shfl_sync(FULL, v, src);
+        const uint32_t wid = __shfl_sync(FULL, id, src);
+        if (improved) {
+          cur_key = key;
+          s.hit_id = (int32_t)wid;
+          s.hit_t = __uint_as_float((uint32_t)(key >> 32));
+          s.hit_u = wu, s.hit_v = wv;
+          s.tmax = x::sub(s.hit_t, eps);  // scene.glsl:116
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      // owners pick up an improvement made by this batch; the winner's u, v, id come by shuffle
-      unsigned long long key = cur_key;
-      if (pooled) key = sm_best[threadIdx.x];
-      const bool improved = key < cur_key;
-      const int src = improved ? (int)(key & 31ull) : (int)lane;
-      const float wu = __shfl_sync(FULL, u, src), wv = __shfl_sync(FULL, v, src);
-      const uint32_t wid = __shfl_sync(FULL, id, src);
-      if (improved) {
-        cur_key = key;
-        s.hit_id = (int32_t)wid;
-        s.hit_t = __uint_as_float((uint32_t)(key >> 32));
-        s.hit_u = wu, s.hit_v = wv;
-        s.tmax = x::sub(s.hit_t, eps);  // scene.glsl:116
-      }
-      __syncwarp();
     }
     // ---- advance / finish (per lane)
     if (active) {
