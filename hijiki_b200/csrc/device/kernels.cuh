@@ -44,7 +44,7 @@ struct WaveDev {
   // per-slot path state
   f4* ray_o;                     // origin.xyz, tMin
   f4* ray_d;                     // direction.xyz, tMax
-  f4* hit;                       // shape id bits, t, u, v
+  f4* hit;                       // shape id bits, t, u, v — indexed by extension-queue position, not by slot
   f4* thr_rng;                   // throughput.rgb, rng state bits
   f4* extinction;                // currentExtinction.rgb (only when the scene can set it)
   // per-pass intermediate layers of the wave, [n_wave_passes][n_pixels]
@@ -181,6 +181,8 @@ struct DevStack {
   __device__ __forceinline__ bool empty() const { return n == 0; }
 };
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Source of rays / sink of results of a traversal launch.  A ray's flavour rides in the top bit of
 // TravState::slot: 1 = any hit (shadow ray), 0 = closest hit (extension ray).
 constexpr uint32_t kAnyHitBit = 0x80000000u;
@@ -198,8 +200,9 @@ struct WaveIO {
       s.slot = i | kAnyHitBit;
       trav_init<GUARD>(s, w.scene, w.sh_o[i], w.sh_d[i]);
     } else {
-      const uint32_t slot = queue[i - n_shadow] & 0x7FFFFFFFu;
-      s.slot = slot;
+      const uint32_t e = i - n_shadow;  // queue position: the hit record goes to hit[e], where k_shade's tile reads it
+      const uint32_t slot = queue[e] & 0x7FFFFFFFu;
+      s.slot = e;
       trav_init<GUARD>(s, w.scene, w.ray_o[slot], w.ray_d[slot]);
     }
   }
@@ -500,6 +503,7 @@ struct TileSort {
   uint32_t warp_count[5][kTileThreads / 32];
   uint32_t n_hits;
   uint32_t entry[kTileThreads];
+  f4 hit[kTileThreads];
 };
 
 __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(WaveDev w, uint32_t bounce) {
@@ -515,10 +519,19 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
     // ---- tile-local material sort
     const uint32_t i = tile * kTileThreads + threadIdx.x;
     uint32_t entry = 0, tag = 0xFFFFFFFFu;
+    f4 h = F4(0.f, 0.f, 0.f, 0.f);
     if (i < n) {
       entry = q[i];
-      const int id = __float_as_int(w.hit[entry & 0x7FFFFFFFu].x);
+      h = w.hit[i];  // k_trace wrote the hit records in queue order: both loads are dense and independent
+      const int id = __float_as_int(h.x);
       if (id >= 0) tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
+    }
+    {  // start the next tile's queue entries and hit records towards L1 while this one is shaded
+      const uint32_t i_next = i + gridDim.x * kTileThreads;
+      if (i_next < n) {
+        if ((threadIdx.x & 7u) == 0) prefetch_l1(q + i_next);  // 8 entries per 32-byte sector
+        if ((threadIdx.x & 1u) == 0) prefetch_l1(w.hit + i_next);
+      }
     }
     uint32_t prefix = 0;
 #pragma unroll
@@ -540,7 +553,11 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
       ts.n_hits = total;
     }
     __syncthreads();
-    if (tag < 5u) ts.entry[ts.warp_count[tag][warp] + prefix] = entry;
+    if (tag < 5u) {
+      const uint32_t pos = ts.warp_count[tag][warp] + prefix;
+      ts.entry[pos] = entry;
+      ts.hit[pos] = h;
+    }
     __syncthreads();
     const uint32_t n_hits = ts.n_hits;
 
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
       VertexIn in;
       in.ray_o = w.ray_o[slot];
       in.ray_d = w.ray_d[slot];
-      const f4 h = w.hit[slot];
+      h = ts.hit[threadIdx.x];
       in.hit_id = __float_as_int(h.x), in.hit_t = h.y, in.hit_u = h.z, in.hit_v = h.w;
       const f4 tr = w.thr_rng[slot];
       in.throughput = xyz(tr);
