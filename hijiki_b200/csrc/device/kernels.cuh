@@ -524,7 +524,14 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
       entry = q[i];
       h = w.hit[i];  // k_trace wrote the hit records in queue order: both loads are dense and independent
       const int id = __float_as_int(h.x);
-      if (id >= 0) tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
+      if (id >= 0) {
+        // the path state is gathered by slot after the sort: start it now, under the sort's barriers
+        // (distinct addresses per thread; prefetching populate()'s vertices the same way was measured
+        // 2x slower on cbox, where whole warps ask for the same wall vertex)
+        const uint32_t sl = entry & 0x7FFFFFFFu;
+        prefetch_l1(w.ray_o + sl), prefetch_l1(w.ray_d + sl), prefetch_l1(w.thr_rng + sl);
+        tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
+      }
     }
     {  // start the next tile's queue entries and hit records towards L1 while this one is shaded
       const uint32_t i_next = i + gridDim.x * kTileThreads;
