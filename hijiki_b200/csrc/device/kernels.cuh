@@ -506,6 +506,35 @@ struct TileSort {
   f4 hit[kTileThreads];
 };
 
+// Front part of a tile: the thread's queue entry, its hit record and material tag (0xFFFFFFFF = miss or
+// past the end).  Issued one tile ahead, between the two barriers of the previous tile's queue append, so the
+// loads travel while that tile waits for its append atomics.
+__device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_t* q, uint32_t n, uint32_t tile,
+                                                 uint32_t& entry, f4& h, uint32_t& tag) {
+  const uint32_t i = tile * kTileThreads + threadIdx.x;
+  entry = 0, tag = 0xFFFFFFFFu;
+  h = F4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) {
+    entry = q[i];
+    h = w.hit[i];  // k_trace wrote the hit records in queue order: both loads are dense and independent
+    const int id = __float_as_int(h.x);
+    if (id >= 0) {
+      // the path state is gathered by slot after the sort: start it now, under the sort's barriers
+      // (distinct addresses per thread; prefetching populate()'s vertices the same way was measured
+      // 2x slower on cbox, where whole warps ask for the same wall vertex)
+      const uint32_t sl = entry & 0x7FFFFFFFu;
+      prefetch_l1(w.ray_o + sl), prefetch_l1(w.ray_d + sl), prefetch_l1(w.thr_rng + sl);
+      tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
+    }
+  }
+  // start the tile after this one towards L1
+  const uint32_t i_next = i + gridDim.x * kTileThreads;
+  if (i_next < n) {
+    if ((threadIdx.x & 7u) == 0) prefetch_l1(q + i_next);  // 8 entries per 32-byte sector
+    if ((threadIdx.x & 1u) == 0) prefetch_l1(w.hit + i_next);
+  }
+}
+
 __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(WaveDev w, uint32_t bounce) {
   __shared__ BlockAppend<2> sm;
   __shared__ TileSort ts;
@@ -513,33 +542,14 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
   const uint32_t n = ctr[CTR_EXT];
   const uint32_t* q = w.ext_q[bounce & 1u];
   uint32_t* next_q = w.ext_q[(bounce + 1u) & 1u];
+  uint32_t* const counter[2] = {ctr + CTR_STRIDE + CTR_EXT, ctr + CTR_SHADOW};
   const uint32_t n_tiles = (n + kTileThreads - 1) / kTileThreads;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t entry = 0, tag = 0xFFFFFFFFu;
+  f4 h = F4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x < n_tiles) shade_tile_front(w, q, n, blockIdx.x, entry, h, tag);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- tile-local material sort
-    const uint32_t i = tile * kTileThreads + threadIdx.x;
-    uint32_t entry = 0, tag = 0xFFFFFFFFu;
-    f4 h = F4(0.f, 0.f, 0.f, 0.f);
-    if (i < n) {
-      entry = q[i];
-      h = w.hit[i];  // k_trace wrote the hit records in queue order: both loads are dense and independent
-      const int id = __float_as_int(h.x);
-      if (id >= 0) {
-        // the path state is gathered by slot after the sort: start it now, under the sort's barriers
-        // (distinct addresses per thread; prefetching populate()'s vertices the same way was measured
-        // 2x slower on cbox, where whole warps ask for the same wall vertex)
-        const uint32_t sl = entry & 0x7FFFFFFFu;
-        prefetch_l1(w.ray_o + sl), prefetch_l1(w.ray_d + sl), prefetch_l1(w.thr_rng + sl);
-        tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
-      }
-    }
-    {  // start the next tile's queue entries and hit records towards L1 while this one is shaded
-      const uint32_t i_next = i + gridDim.x * kTileThreads;
-      if (i_next < n) {
-        if ((threadIdx.x & 7u) == 0) prefetch_l1(q + i_next);  // 8 entries per 32-byte sector
-        if ((threadIdx.x & 1u) == 0) prefetch_l1(w.hit + i_next);
-      }
-    }
     uint32_t prefix = 0;
 #pragma unroll
     for (uint32_t t = 0; t < 5; t++) {
@@ -602,16 +612,35 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
         if (w.has_extinction) w.extinction[slot] = F4(out.extinction.x, out.extinction.y, out.extinction.z, 0.f);
       }
     }
-    const bool flag[2] = {want_next, want_shadow};
-    uint32_t* const c[2] = {ctr + CTR_STRIDE + CTR_EXT, ctr + CTR_SHADOW};
-    uint32_t pos[2];
-    block_append<2, false>(sm, flag, c, pos);  // the next tile's sort barriers protect `sm` and `ts`
-    if (want_next) next_q[pos[0]] = slot | (out.was_discrete ? 0x80000000u : 0u);
-    if (want_shadow) {
-      w.sh_o[pos[1]] = out.sh_o;
-      w.sh_d[pos[1]] = out.sh_d;
-      w.sh_c[pos[1]] = F4(out.contribution.x, out.contribution.y, out.contribution.z, __uint_as_float(slot));
+
+    // ---- append to the next extension queue and the shadow queue: one atomic per CTA per queue.  The next
+    // tile's front loads are issued between the two barriers, while threads 0 and 1 wait for the atomics.
+    const uint32_t b_next = __ballot_sync(0xFFFFFFFFu, want_next), b_sh = __ballot_sync(0xFFFFFFFFu, want_shadow);
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t pre_next = __popc(b_next & below), pre_sh = __popc(b_sh & below);
+    if (lane == 0) sm.warp_total[0][warp] = __popc(b_next), sm.warp_total[1][warp] = __popc(b_sh);
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      uint32_t total = 0;
+      for (uint32_t wi = 0; wi < kTileThreads / 32; wi++) {
+        const uint32_t c = sm.warp_total[threadIdx.x][wi];
+        sm.warp_total[threadIdx.x][wi] = total;
+        total += c;
+      }
+      sm.base[threadIdx.x] = total ? atomicAdd(counter[threadIdx.x], total) : 0u;
     }
+    const uint32_t tile_next = tile + gridDim.x;
+    const bool was_discrete = out.was_discrete;
+    if (tile_next < n_tiles) shade_tile_front(w, q, n, tile_next, entry, h, tag);
+    __syncthreads();
+    if (want_next) next_q[sm.base[0] + sm.warp_total[0][warp] + pre_next] = slot | (was_discrete ? 0x80000000u : 0u);
+    if (want_shadow) {
+      const uint32_t pos = sm.base[1] + sm.warp_total[1][warp] + pre_sh;
+      w.sh_o[pos] = out.sh_o;
+      w.sh_d[pos] = out.sh_d;
+      w.sh_c[pos] = F4(out.contribution.x, out.contribution.y, out.contribution.z, __uint_as_float(slot));
+    }
+    // (sm and ts are next written after the following tile's sort barriers / read before them)
   }
 }
 
