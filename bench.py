@@ -460,7 +460,9 @@ def main():
             "clocks": clocks,
             "exact_ties": {"value": exact_rays / (exact_ms * 1e-3) / 1e6 if exact_ms else None, "unit": "Mrays/s",
                            "unresolved_clusters_last_step": exact_unresolved,
-                           "note": "this rank, 2 steps, HJK_RENDER_EXACT_TIES: frames bit-identical to the oracle"},
+                           "note": "this rank, 2 steps, HJK_RENDER_EXACT_TIES (the mode whose frames the parity tests "
+                                   "hold bit-identical to the oracle); unresolved = tie clusters longer than the "
+                                   "8*M_EPS window or 12 candidates, counted, each can move one sample"},
         }
         if e2e_ms is not None:
             line["e2e"] = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",

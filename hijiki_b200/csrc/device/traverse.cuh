@@ -265,6 +265,16 @@ struct TieCands {
   uint32_t n;
   uint32_t unresolved;
   HJK_HD void reset() { n = 0, unresolved = 0; }
+  // drops the candidates the nearest hit has since left behind (t beyond its window)
+  HJK_HD void prune(float t_cull) {
+    uint32_t m = 0;
+    for (uint32_t k = 0; k < n; k++)
+      if (t[k] <= t_cull) {
+        t[m] = t[k], id[m] = id[k], prim[m] = prim[k];
+        m++;
+      }
+    n = m;
+  }
   HJK_HD void add(float tt, uint32_t i, uint32_t p) {
     if (n < (uint32_t)kTieCands) {
       t[n] = tt, id[n] = i, prim[n] = p;
@@ -276,9 +286,12 @@ struct TieCands {
 };
 struct NoCands {  // default mode: nothing is recorded
   HJK_HD void reset() {}
+  HJK_HD void prune(float) {}
   HJK_HD void add(float, uint32_t, uint32_t) {}
 };
 HJK_HD uint32_t cands_unresolved(const TieCands& c) { return c.unresolved; }
+HJK_HD bool cands_full(const TieCands& c) { return c.n == (uint32_t)kTieCands; }
+HJK_HD bool cands_full(const NoCands&) { return false; }
 HJK_HD uint32_t cands_unresolved(const NoCands&) { return 0u; }
 
 // Forward declaration (defined below with the primitive tests).
@@ -396,12 +409,13 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
         }
         if (EXACT) {
           if (t <= s.t_cull) {
-            cands.add(t, x::as_uint(r0.w), prim_index);
             if (s.hit_id < 0 || t < s.hit_t) {
               s.hit_id = (int32_t)x::as_uint(r0.w);
               s.hit_t = t, s.hit_u = u, s.hit_v = v;
               s.t_cull = x::add(t, x::mul(kTieWindowEps, eps));
             }
+            if (cands_full(cands)) cands.prune(s.t_cull);  // far-to-near visiting order leaves stale entries
+            cands.add(t, x::as_uint(r0.w), prim_index);
           }
         } else {
           s.hit_id = (int32_t)x::as_uint(r0.w);
