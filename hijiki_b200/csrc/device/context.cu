@@ -124,7 +124,7 @@ struct HjkContext {
   DevBuf<f4> d_acc, d_norm;
 
   // wave buffers
-  DevBuf<f4> d_ray_o, d_ray_d, d_hit, d_thr, d_ext, d_layer0, d_layer1, d_sh_o, d_sh_d, d_sh_c;
+  DevBuf<f4> d_ray_o[2], d_ray_d[2], d_thr[2], d_ext[2], d_hit, d_layer0, d_layer1, d_sh_o, d_sh_d, d_sh_c;
   DevBuf<uint32_t> d_ext_q0, d_ext_q1, d_counters;
   DevBuf<unsigned long long> d_totals;  // paths, extension rays, shadow rays of the current call
   DevBuf<uint32_t> d_unresolved;        // exact-tie mode: rays whose cluster outgrew the window/list
@@ -282,11 +282,13 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   const bool do_recon = !(prm->flags & HJK_RENDER_NO_RECON);
   if (do_recon && R > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
 
-  HJK_CUDA(c, c->d_ray_o.ensure(n_slots));
-  HJK_CUDA(c, c->d_ray_d.ensure(n_slots));
+  for (int par = 0; par < 2; par++) {  // queue-ordered path state, ping-pong by bounce parity
+    HJK_CUDA(c, c->d_ray_o[par].ensure(n_slots));
+    HJK_CUDA(c, c->d_ray_d[par].ensure(n_slots));
+    HJK_CUDA(c, c->d_thr[par].ensure(n_slots));
+    if (c->has_extinction) HJK_CUDA(c, c->d_ext[par].ensure(n_slots));
+  }
   HJK_CUDA(c, c->d_hit.ensure(n_slots));
-  HJK_CUDA(c, c->d_thr.ensure(n_slots));
-  if (c->has_extinction) HJK_CUDA(c, c->d_ext.ensure(n_slots));
   HJK_CUDA(c, c->d_layer0.ensure(n_slots));
   HJK_CUDA(c, c->d_layer1.ensure(n_slots));
   HJK_CUDA(c, c->d_sh_o.ensure(n_slots));
@@ -326,8 +328,11 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.tile_w = plan.tile_w, w.tile_h = plan.tile_h, w.tiles_x = plan.tiles_x, w.tiles_y = plan.tiles_y;
   w.blocks = d_blocks;
   w.weights = c->d_weights.p;
-  w.ray_o = c->d_ray_o.p, w.ray_d = c->d_ray_d.p, w.hit = c->d_hit.p, w.thr_rng = c->d_thr.p;
-  w.extinction = c->d_ext.p;
+  for (int par = 0; par < 2; par++) {
+    w.ray_o[par] = c->d_ray_o[par].p, w.ray_d[par] = c->d_ray_d[par].p, w.thr_rng[par] = c->d_thr[par].p;
+    w.extinction[par] = c->d_ext[par].p;
+  }
+  w.hit = c->d_hit.p;
   w.layer0 = c->d_layer0.p, w.layer1 = c->d_layer1.p;
   w.ext_q[0] = c->d_ext_q0.p, w.ext_q[1] = c->d_ext_q1.p;
   w.sh_o = c->d_sh_o.p, w.sh_d = c->d_sh_d.p, w.sh_c = c->d_sh_c.p;

@@ -41,12 +41,13 @@ struct WaveDev {
   const int32_t* tile_block;     // [n_wave_passes][tiles_y*tiles_x] -> index into blocks
   const HjkImageBlock* blocks;   // the whole block list of the call
   const float* weights;          // [(2R+1)^2] per block
-  // per-slot path state
-  f4* ray_o;                     // origin.xyz, tMin
-  f4* ray_d;                     // direction.xyz, tMax
-  f4* hit;                       // shape id bits, t, u, v — indexed by extension-queue position, not by slot
-  f4* thr_rng;                   // throughput.rgb, rng state bits
-  f4* extinction;                // currentExtinction.rgb (only when the scene can set it)
+  // path state, queue-ordered: element e belongs to the path at position e of the bounce's extension
+  // queue (compacted every bounce by k_shade; [bounce & 1] is read, [(bounce + 1) & 1] written)
+  f4* ray_o[2];                  // origin.xyz, tMin
+  f4* ray_d[2];                  // direction.xyz, tMax
+  f4* thr_rng[2];                // throughput.rgb, rng state bits
+  f4* extinction[2];             // currentExtinction.rgb (only when the scene can set it)
+  f4* hit;                       // shape id bits, t, u, v
   // per-pass intermediate layers of the wave, [n_wave_passes][n_pixels]
   f4* layer0;                    // (radiance, 1)      render.glsl:172
   f4* layer1;                    // (normal, depth)    render.glsl:173
@@ -129,6 +130,8 @@ __global__ void __launch_bounds__(kTileThreads) k_raygen(WaveDev w) {
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t slot = tile * kTileThreads + threadIdx.x;
     bool valid = false;
+    f4 o = F4(0.f, 0.f, 0.f, 0.f), d = o;
+    uint32_t rng = 0;
     if (slot < w.n_slots) {
       const uint32_t wp = slot / w.n_pixels, pix = slot - wp * w.n_pixels;
       const uint32_t gy = pix / w.width, gx = pix - gy * w.width;
@@ -138,15 +141,10 @@ __global__ void __launch_bounds__(kTileThreads) k_raygen(WaveDev w) {
         const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];
         if (lx < blk.dimension[0] && ly < blk.dimension[1]) {
           valid = true;
-          const uint32_t rng = seed_rng(blk.seed + lx + ly * blk.dimension[0]);  // render.glsl:156
-          f4 o, d;
+          rng = seed_rng(blk.seed + lx + ly * blk.dimension[0]);  // render.glsl:156
           camera_ray(w.scene.camera, x::add((float)gx, blk.sample_offset[0]),
                      x::add((float)gy, blk.sample_offset[1]), (float)blk.original_dimension[0],
                      (float)blk.original_dimension[1], w.eps, o, d);
-          w.ray_o[slot] = o;
-          w.ray_d[slot] = d;
-          w.thr_rng[slot] = F4(1.f, 1.f, 1.f, __uint_as_float(rng));
-          if (w.has_extinction) w.extinction[slot] = F4(0.f, 0.f, 0.f, 0.f);
         }
       }
       w.layer0[slot] = F4(0.f, 0.f, 0.f, valid ? 1.f : 0.f);
@@ -156,7 +154,14 @@ __global__ void __launch_bounds__(kTileThreads) k_raygen(WaveDev w) {
     uint32_t* const ctr[1] = {w.counters + CTR_EXT};
     uint32_t pos[1];
     block_append<1>(sm, flag, ctr, pos);
-    if (valid) w.ext_q[0][pos[0]] = slot | 0x80000000u;  // wasDiscrete = true (render.glsl:91)
+    if (valid) {  // the path state lives at the path's queue position
+      const uint32_t e = pos[0];
+      w.ext_q[0][e] = slot | 0x80000000u;  // wasDiscrete = true (render.glsl:91)
+      w.ray_o[0][e] = o;
+      w.ray_d[0][e] = d;
+      w.thr_rng[0][e] = F4(1.f, 1.f, 1.f, __uint_as_float(rng));
+      if (w.has_extinction) w.extinction[0][e] = F4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -192,7 +197,8 @@ constexpr uint32_t kAnyHitBit = 0x80000000u;
 // launch has one tail instead of two and shadow rays fill the lanes extension rays leave idle.
 struct WaveIO {
   const WaveDev& w;
-  const uint32_t* queue;  // extension queue of this bounce
+  const f4* ray_o;  // extension rays of this bounce, in queue order
+  const f4* ray_d;
   uint32_t n_shadow;
   template <bool GUARD>
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
@@ -200,10 +206,9 @@ struct WaveIO {
       s.slot = i | kAnyHitBit;
       trav_init<GUARD>(s, w.scene, w.sh_o[i], w.sh_d[i]);
     } else {
-      const uint32_t e = i - n_shadow;  // queue position: the hit record goes to hit[e], where k_shade's tile reads it
-      const uint32_t slot = queue[e] & 0x7FFFFFFFu;
+      const uint32_t e = i - n_shadow;  // queue position: ray and hit record live there (dense, no indirection)
       s.slot = e;
-      trav_init<GUARD>(s, w.scene, w.ray_o[slot], w.ray_d[slot]);
+      trav_init<GUARD>(s, w.scene, ray_o[e], ray_d[e]);
     }
   }
   __device__ __forceinline__ void store(const TravState& s) const {
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
-  const WaveIO io{w, w.ext_q[bounce & 1u], n_shadow};
+  const WaveIO io{w, w.ray_o[bounce & 1u], w.ray_d[bounce & 1u], n_shadow};
   traverse_queue<GUARD, EXACT>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
                                (int)w.postpone_lanes, w.unresolved);
 }
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(kTravThreads, 8) k_trace_coop(WaveDev w, uint3
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
-  const WaveIO io{w, w.ext_q[bounce & 1u], n_shadow};
+  const WaveIO io{w, w.ray_o[bounce & 1u], w.ray_d[bounce & 1u], n_shadow};
   traverse_queue_coop<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
                              w.coop_batch_cost);
 }
@@ -503,6 +508,7 @@ struct TileSort {
   uint32_t warp_count[5][kTileThreads / 32];
   uint32_t n_hits;
   uint32_t entry[kTileThreads];
+  uint32_t src[kTileThreads];  // position in the tile before the sort (the path state is read from there)
   f4 hit[kTileThreads];
 };
 
@@ -510,7 +516,7 @@ struct TileSort {
 // past the end).  Issued one tile ahead, between the two barriers of the previous tile's queue append, so the
 // loads travel while that tile waits for its append atomics.
 __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_t* q, uint32_t n, uint32_t tile,
-                                                 uint32_t& entry, f4& h, uint32_t& tag) {
+                                                 uint32_t bounce, uint32_t& entry, f4& h, uint32_t& tag) {
   const uint32_t i = tile * kTileThreads + threadIdx.x;
   entry = 0, tag = 0xFFFFFFFFu;
   h = F4(0.f, 0.f, 0.f, 0.f);
@@ -518,20 +524,17 @@ __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_
     entry = q[i];
     h = w.hit[i];  // k_trace wrote the hit records in queue order: both loads are dense and independent
     const int id = __float_as_int(h.x);
-    if (id >= 0) {
-      // the path state is gathered by slot after the sort: start it now, under the sort's barriers
-      // (distinct addresses per thread; prefetching populate()'s vertices the same way was measured
-      // 2x slower on cbox, where whole warps ask for the same wall vertex)
-      const uint32_t sl = entry & 0x7FFFFFFFu;
-      prefetch_l1(w.ray_o + sl), prefetch_l1(w.ray_d + sl), prefetch_l1(w.thr_rng + sl);
-      tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
-    }
+    if (id >= 0) tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
   }
   // start the tile after this one towards L1
   const uint32_t i_next = i + gridDim.x * kTileThreads;
   if (i_next < n) {
     if ((threadIdx.x & 7u) == 0) prefetch_l1(q + i_next);  // 8 entries per 32-byte sector
-    if ((threadIdx.x & 1u) == 0) prefetch_l1(w.hit + i_next);
+    if ((threadIdx.x & 1u) == 0) {
+      prefetch_l1(w.hit + i_next);
+      prefetch_l1(w.ray_o[bounce & 1u] + i_next), prefetch_l1(w.ray_d[bounce & 1u] + i_next);
+      prefetch_l1(w.thr_rng[bounce & 1u] + i_next);
+    }
   }
 }
 
@@ -544,10 +547,10 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
   uint32_t* next_q = w.ext_q[(bounce + 1u) & 1u];
   uint32_t* const counter[2] = {ctr + CTR_STRIDE + CTR_EXT, ctr + CTR_SHADOW};
   const uint32_t n_tiles = (n + kTileThreads - 1) / kTileThreads;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, par = bounce & 1u;
   uint32_t entry = 0, tag = 0xFFFFFFFFu;
   f4 h = F4(0.f, 0.f, 0.f, 0.f);
-  if (blockIdx.x < n_tiles) shade_tile_front(w, q, n, blockIdx.x, entry, h, tag);
+  if (blockIdx.x < n_tiles) shade_tile_front(w, q, n, blockIdx.x, bounce, entry, h, tag);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- tile-local material sort
     uint32_t prefix = 0;
@@ -573,6 +576,7 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
     if (tag < 5u) {
       const uint32_t pos = ts.warp_count[tag][warp] + prefix;
       ts.entry[pos] = entry;
+      ts.src[pos] = threadIdx.x;
       ts.hit[pos] = h;
     }
     __syncthreads();
@@ -585,15 +589,16 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
     if (threadIdx.x < n_hits) {
       entry = ts.entry[threadIdx.x];
       slot = entry & 0x7FFFFFFFu;
+      const uint32_t e = tile * kTileThreads + ts.src[threadIdx.x];
       VertexIn in;
-      in.ray_o = w.ray_o[slot];
-      in.ray_d = w.ray_d[slot];
+      in.ray_o = w.ray_o[par][e];
+      in.ray_d = w.ray_d[par][e];
       h = ts.hit[threadIdx.x];
       in.hit_id = __float_as_int(h.x), in.hit_t = h.y, in.hit_u = h.z, in.hit_v = h.w;
-      const f4 tr = w.thr_rng[slot];
+      const f4 tr = w.thr_rng[par][e];
       in.throughput = xyz(tr);
       in.rng = __float_as_uint(tr.w);
-      in.extinction = w.has_extinction ? xyz(w.extinction[slot]) : V3(0.f);
+      in.extinction = w.has_extinction ? xyz(w.extinction[par][e]) : V3(0.f);
       in.was_discrete = (entry >> 31) != 0u;
       in.bounce = bounce;
       shade_vertex(w.scene, in, w.max_bounces, w.rr_start, w.eps, out);
@@ -605,12 +610,6 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
       }
       want_next = out.continues;
       want_shadow = out.has_shadow;
-      if (want_next) {
-        w.ray_o[slot] = out.next_o;
-        w.ray_d[slot] = out.next_d;
-        w.thr_rng[slot] = F4(out.throughput.x, out.throughput.y, out.throughput.z, __uint_as_float(out.rng));
-        if (w.has_extinction) w.extinction[slot] = F4(out.extinction.x, out.extinction.y, out.extinction.z, 0.f);
-      }
     }
 
     // ---- append to the next extension queue and the shadow queue: one atomic per CTA per queue.  The next
@@ -631,9 +630,16 @@ __global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(Wav
     }
     const uint32_t tile_next = tile + gridDim.x;
     const bool was_discrete = out.was_discrete;
-    if (tile_next < n_tiles) shade_tile_front(w, q, n, tile_next, entry, h, tag);
+    if (tile_next < n_tiles) shade_tile_front(w, q, n, tile_next, bounce, entry, h, tag);
     __syncthreads();
-    if (want_next) next_q[sm.base[0] + sm.warp_total[0][warp] + pre_next] = slot | (was_discrete ? 0x80000000u : 0u);
+    if (want_next) {  // the surviving path moves to its position in the next queue
+      const uint32_t e = sm.base[0] + sm.warp_total[0][warp] + pre_next;
+      next_q[e] = slot | (was_discrete ? 0x80000000u : 0u);
+      w.ray_o[par ^ 1u][e] = out.next_o;
+      w.ray_d[par ^ 1u][e] = out.next_d;
+      w.thr_rng[par ^ 1u][e] = F4(out.throughput.x, out.throughput.y, out.throughput.z, __uint_as_float(out.rng));
+      if (w.has_extinction) w.extinction[par ^ 1u][e] = F4(out.extinction.x, out.extinction.y, out.extinction.z, 0.f);
+    }
     if (want_shadow) {
       const uint32_t pos = sm.base[1] + sm.warp_total[1][warp] + pre_sh;
       w.sh_o[pos] = out.sh_o;
