@@ -84,6 +84,9 @@ constexpr int kPostponeLanes = 8;    // postpone primitive tests that fewer lane
 #define HJK_TILE_THREADS 256
 #endif
 constexpr int kTileThreads = HJK_TILE_THREADS;
+#ifndef HJK_SHADE_MIN_BLOCKS
+#define HJK_SHADE_MIN_BLOCKS (1024 / HJK_TILE_THREADS)
+#endif
 
 // ---------------------------------------------------------------- block-level compaction
 // Every thread of the block calls this (flag may be false).  Returns the global position
@@ -538,7 +541,7 @@ __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads, 1024 / kTileThreads) k_shade(WaveDev w, uint32_t bounce) {
+__global__ void __launch_bounds__(kTileThreads, HJK_SHADE_MIN_BLOCKS) k_shade(WaveDev w, uint32_t bounce) {
   __shared__ BlockAppend<2> sm;
   __shared__ TileSort ts;
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
