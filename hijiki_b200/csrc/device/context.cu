@@ -1077,8 +1077,8 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "postpone_lanes") {
     if (value < 0 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->postpone_lanes = (uint32_t)value;
-  } else if (k == "blocks_per_sm_traverse") {
-    if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+  } else if (k == "blocks_per_sm_traverse") {  // 0 = the occupancy of each trace kernel
+    if (value < 0 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->blocks_trav_override = (int)value;
   } else if (k == "blocks_per_sm_tile") {
     if (value < 1 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");

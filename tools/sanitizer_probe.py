@@ -21,6 +21,21 @@ for builder in (0, 1):
         rays["t_min"], rays["t_max"] = 1e-4, np.inf
         ctx.trace_first_hit(rays); ctx.trace_first_hit(rays, any_hit=True); ctx.trace_first_hit(rays, exact_ties=True)
         print("ok", builder, st.n_rays, float(img[..., :3].mean()), flush=True)
+# several tiles per CTA (grid-stride loops, the software pipeline of k_shade) and both trace kernels
+ctx.set_option("bvh_builder", 0)
+ctx.scene_upload(hj.Scene.from_obj("scenes/cbox/cbox.obj", put_cbox_spheres=True).compile())
+tile_blocks = ctx.get_info("blocks_per_sm_tile")
+ctx.set_option("blocks_per_sm_tile", 1)
+ctx.set_option("blocks_per_sm_traverse", 1)
+for coop in (1, 0):
+    ctx.set_option("coop_trace", coop)
+    blocks = hj.ImageBlockGenerator(320, 200, 64, 3).blocks()
+    ctx.frame_begin(320, 200)
+    st = ctx.render(blocks, hj.make_params(max_bounces=5))
+    print("multi-tile ok", coop, st.n_rays, flush=True)
+ctx.set_option("coop_trace", 1)
+ctx.set_option("blocks_per_sm_tile", tile_blocks)
+ctx.set_option("blocks_per_sm_traverse", 0)
 rad = np.ones((72, 96, 4), np.float32); nrm = np.zeros((72, 96, 4), np.float32); nrm[..., 2] = 1
 ctx.frame_begin(96, 72)
 ctx.denoise_pass(rad, nrm, rad, hj.ImageBlockGenerator(96, 72, 64, 1).blocks(), hj.make_params())
