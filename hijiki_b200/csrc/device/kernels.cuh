@@ -662,7 +662,13 @@ __global__ void k_recon_weights(const HjkImageBlock* blocks, uint32_t n_blocks, 
                             taps + (size_t)b * recon_tap_stride(radius));
 }
 
-constexpr int kReconTileX = 32, kReconTileY = 16;
+#ifndef HJK_RECON_TILE_Y
+#define HJK_RECON_TILE_Y 8
+#endif
+#ifndef HJK_RECON_MIN_BLOCKS
+#define HJK_RECON_MIN_BLOCKS 6
+#endif
+constexpr int kReconTileX = 32, kReconTileY = HJK_RECON_TILE_Y;  // recon_smem_pitch() assumes 32
 
 struct SmemLayers {  // tile + halo staged in shared memory
   const f4* s0;
@@ -680,16 +686,54 @@ struct SmemLayers {  // tile + halo staged in shared memory
   }
 };
 
+// Interior texels (at least R away from every edge of their block: 94 % of a 128 x 128 block at R = 2) see
+// exactly one block and all of its taps: same taps, same order, same arithmetic as reconstruct_pixel, without
+// the per-tap bounds tests, coordinate unpacking and tile lookups (the shared-memory offset of a tap comes
+// precomputed in the tap table): 18 % fewer instructions.  The kernel is latency-bound, not issue-bound:
+// what paid was occupancy — 32 x 8 tiles at 40 registers, 6 CTAs = 48 warps per SM (990 -> 1244 GB/s at 4K;
+// measured 16-row tiles x 2/3/4 CTAs and 8-row tiles x 4/5/6/7/8 CTAs); keeping two taps in flight per
+// thread changed nothing.
+template <bool HAS_ALBEDO>
+__device__ __forceinline__ f4 recon_tap_weighted(uint2 tw, const f4* s0, const f4* s1, const f4* s2, int cidx, vec3 nc,
+                                                 vec3 ac) {
+  const int idx = cidx + ((int)tw.y >> 16);
+  float w = __uint_as_float(tw.x);
+  const f4 cw = s0[idx];
+  const vec3 no = xyz(s1[idx]) - nc;
+  float e = x::mul(dot(no, no), 2.0f);
+  if (HAS_ALBEDO) {
+    const vec3 ao = xyz(s2[idx]) - ac;
+    e = x::add(e, dot(ao, ao));
+  }
+  if (e != 0.f) w = x::mul(w, exp_det_neg(e));  // exp_det(-0) == 1 exactly, so the branch only saves work
+  return F4(x::mul(w, cw.x), x::mul(w, cw.y), x::mul(w, cw.z), x::mul(w, cw.w));
+}
+__device__ __forceinline__ f4 recon_accumulate(f4 acc, f4 wv) {  // reconstruction.glsl:55-58: NaN samples are dropped
+  if (x::is_nan(wv.x) || x::is_nan(wv.y) || x::is_nan(wv.z) || x::is_nan(wv.w)) return acc;
+  return F4(x::add(acc.x, wv.x), x::add(acc.y, wv.y), x::add(acc.z, wv.z), x::add(acc.w, wv.w));
+}
+template <bool HAS_ALBEDO>
+__device__ __forceinline__ f4 reconstruct_interior(const uint32_t* tl, const f4* s0, const f4* s1, const f4* s2,
+                                                   int cidx, f4 acc) {
+  const vec3 nc = xyz(s1[cidx]);
+  const vec3 ac = HAS_ALBEDO ? xyz(s2[cidx]) : V3(0.f);
+  const uint32_t n = tl[0];
+  const uint2* tp = reinterpret_cast<const uint2*>(tl + 2);
+  for (uint32_t k = 0; k < n; k++)
+    acc = recon_accumulate(acc, recon_tap_weighted<HAS_ALBEDO>(__ldg(tp + k), s0, s1, s2, cidx, nc, ac));
+  return acc;
+}
+
 // One launch reconstructs `n_passes` consecutive passes (layers [pass][pixel]): the
 // accumulator texel stays in a register across passes, each pass' tile is staged once.
 // pass_tile_block advances by tiles_x*tiles_y per pass.  albedo may be null.
 template <bool HAS_ALBEDO>
-__global__ void __launch_bounds__(kReconTileX* kReconTileY)
+__global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS)
     k_recon(PassDev ps, uint32_t n_passes, const f4* __restrict__ layer0, const f4* __restrict__ layer1,
             const f4* __restrict__ layer2, f4* __restrict__ accumulator) {
   extern __shared__ f4 smem[];
   const int R = ps.radius;
-  const int pitch = kReconTileX + 2 * R, rows = kReconTileY + 2 * R;
+  const int pitch = recon_smem_pitch(R), rows = kReconTileY + 2 * R;
   f4* s0 = smem;
   f4* s1 = s0 + pitch * rows;
   f4* s2 = s1 + pitch * rows;
@@ -724,8 +768,21 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY)
     }
     __syncthreads();
     if (in_image) {
-      const SmemLayers L{s0, s1, s2, x0, y0, pitch};
-      acc = reconstruct_pixel<HAS_ALBEDO>(ps, L, gx, gy, acc);
+      const int32_t b = ps.tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
+      bool interior = false;
+      if (b >= 0) {
+        const HjkImageBlock& blk = ps.blocks[b];
+        const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];  // >= 0: block origins sit on the tile grid
+        interior = lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
+                   ly + (uint32_t)R < blk.dimension[1];
+      }
+      if (interior) {
+        const int cidx = ((int)gy - y0) * pitch + ((int)gx - x0);
+        acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R), s0, s1, s2, cidx, acc);
+      } else {
+        const SmemLayers L{s0, s1, s2, x0, y0, pitch};
+        acc = reconstruct_pixel<HAS_ALBEDO>(ps, L, gx, gy, acc);
+      }
     }
     __syncthreads();
     ps.tile_block += (size_t)ps.tiles_x * ps.tiles_y;

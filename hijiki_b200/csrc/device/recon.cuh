@@ -23,9 +23,12 @@ struct PassDev {
   const float* weights;        // [(2R+1)^2] spatial weights per block, dx-major; < 0 = skipped tap
   const uint32_t* taps;        // per block: {count, 0}, then (2R+1)^2 x {weight bits, packed offset} of the
                                // taps with weight >= 0 in loop order (recon_tap_stride words per block,
-                               // 8-byte aligned pairs)
+                               // 8-byte aligned pairs); packed offset = (dx+128) | (dy+128) << 8 |
+                               // int16(dy * kReconSmemPitch(R) + dx) << 16 (k_recon's shared-memory tile)
   int32_t radius;
 };
+// pitch of k_recon's shared-memory tile (32 texels + halo); baked into the tap table
+HJK_HD int recon_smem_pitch(int radius) { return 32 + 2 * radius; }
 HJK_HD uint32_t recon_tap_stride(int radius) { return 2u + 2u * (uint32_t)((2 * radius + 1) * (2 * radius + 1)); }
 
 // spatial weight of tap (dx, dy) for a block's sample offset — reconstruction.glsl:29-30,43-46
@@ -49,7 +52,8 @@ HJK_HD void recon_fill_block_tables(const HjkImageBlock& blk, int radius, float 
       weights[(dx + radius) * t + (dy + radius)] = w;
       if (w < 0.f) continue;
       taps[2 + 2 * n] = x::as_uint(w);
-      taps[3 + 2 * n] = (uint32_t)(dx + 128) | ((uint32_t)(dy + 128) << 8);
+      taps[3 + 2 * n] = (uint32_t)(dx + 128) | ((uint32_t)(dy + 128) << 8) |
+                        ((uint32_t)(uint16_t)(int16_t)(dy * recon_smem_pitch(radius) + dx) << 16);
       n++;
     }
   taps[0] = n;
