@@ -68,6 +68,9 @@ struct WaveDev {
   uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
 };
 
+#ifndef HJK_TRACE_COOP_MIN_BLOCKS
+#define HJK_TRACE_COOP_MIN_BLOCKS 9  // measured 7/8/9/10: 33.9 / 32.8 / 32.4 / 39.1 ms per step on cbox
+#endif
 #ifndef HJK_TRACE_MIN_BLOCKS
 #define HJK_TRACE_MIN_BLOCKS 9 /* 56 registers, no spills: 36 warps per SM (measured best of 8/9/10/12) */
 #endif
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS
 }
 // same work, pooled primitive tests (traverse_queue_coop)
 template <bool GUARD>
-__global__ void __launch_bounds__(kTravThreads, 8) k_trace_coop(WaveDev w, uint32_t bounce, uint32_t last) {
+__global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_COOP_MIN_BLOCKS) k_trace_coop(WaveDev w, uint32_t bounce, uint32_t last) {
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
