@@ -179,7 +179,7 @@ def run_reference(args, rank, wl):
     if kind == "terrain":
         base["unavailable"] = ("the reference's flattened BVH uses exit index 1000000 as its end sentinel "
                                "(src/main.rs:231) and cannot represent a 10 M-triangle scene")
-        print(json.dumps(base), flush=True)
+        emit(base)
         return
     run, blocks, bpp, cores = _oracle_setup(wl)
     mid = bpp // 2
@@ -205,7 +205,7 @@ def run_reference(args, rank, wl):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
-    print(json.dumps(base), flush=True)
+    emit(base)
 
 
 def cpu_baseline_sample(wl):
@@ -226,7 +226,31 @@ def cpu_baseline_sample(wl):
 
 
 # ------------------------------------------------------------------------------ our arm
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    the first communicator), so everything but the result line is sent to stderr: fd 1 is pointed at fd 2 and
+    the original stdout kept for emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -476,7 +500,7 @@ def main():
             line["denoiser"] = denoiser
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(wl)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
