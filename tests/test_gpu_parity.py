@@ -168,6 +168,41 @@ def test_denoise_pass_matches_oracle(gpu_ctx):
         assert np.array_equal(acc_o.view(np.uint32), gpu_ctx.readback(normalise=False).view(np.uint32))
 
 
+@pytest.mark.parametrize("w,h,bs,radius,stddev", [
+    (37, 41, 16, 0, 0.5), (150, 70, 64, 1, 0.5), (257, 130, 128, 3, 1.5), (96, 64, 32, 5, 2.0), (130, 75, 64, 8, 3.0),
+    (33, 9, 8, 2, 0.5),  # blocks narrower than 2R + 1 texels of interior: every texel takes the general path
+])
+def test_reconstruction_shapes_match_oracle(gpu_ctx, w, h, bs, radius, stddev):
+    """k_recon's interior fast path and its general (block edge / apron) path against the oracle, bit for bit:
+    radii 0..8, image sizes that are no multiple of the 32x8 CUDA tile, blocks from 8 to 128 texels."""
+    rng = np.random.default_rng(w * 1000 + h)
+    # two passes of bs x bs blocks (the reference's generator only makes multiples of 64)
+    blocks = np.zeros(2 * ((w + bs - 1) // bs) * ((h + bs - 1) // bs), dtype=_abi.BLOCK_DTYPE)
+    k = 0
+    for p in range(2):
+        so = rng.random(2).astype(np.float32)
+        for by in range(0, h, bs):
+            for bx in range(0, w, bs):
+                blocks[k] = (k, 1000 + k, (bx, by), (min(bs, w - bx), min(bs, h - by)), (w, h), so)
+                k += 1
+    rad = np.exp(rng.standard_normal((h, w, 4))).astype(np.float32)
+    rad[..., 3] = 1.0
+    rad[h // 2, w // 3, 1] = np.nan
+    nrm = rng.standard_normal((h, w, 4)).astype(np.float32)
+    nrm[..., :3] /= np.linalg.norm(nrm[..., :3], axis=2, keepdims=True)
+    nrm[: h // 2, : w // 2, :3] = (0.0, 1.0, 0.0)  # a flat region: identical normals, the exp is skipped
+    O = _libs.oracle()
+    gpu_ctx.frame_begin(w, h)
+    acc_o = np.zeros((h, w, 4), np.float32)
+    op = _libs.orc_params(block_size=bs, radius=radius, stddev=stddev)
+    for one_pass in np.split(blocks, 2):  # a denoise call takes one pass; the second call accumulates
+        one_pass = np.ascontiguousarray(one_pass)
+        gpu_ctx.denoise_pass(rad, nrm, None, one_pass, hj.make_params(recon_radius=radius, recon_stddev=stddev))
+        assert O.orc_reconstruct_frame(_libs.ptr(one_pass), one_pass.size, C.byref(op), _libs.ptr(rad), _libs.ptr(nrm),
+                                       None, _libs.ptr(acc_o), 0) == 0
+    assert np.array_equal(acc_o.view(np.uint32), gpu_ctx.readback(normalise=False).view(np.uint32))
+
+
 def test_device_math_matches_spec_bitwise(gpu_ctx):
     """The device build of hjk_math.cuh == oracle/orc_math.h, through the only place it surfaces
     directly: the reconstruction weights (exp) — checked via a one-texel splat."""
