@@ -58,10 +58,10 @@ EXTEND_BYTES_PER_RAY = 4 + 32 + 16
 SHADOW_BYTES_PER_RAY = 32 + 16
 PIPE_BYTES_EXT, PIPE_BYTES_SHADOW = 192, 96
 RECON_BYTES_PER_PX = 64  # 2 x 16 B layers + accumulator read + write (the all-zero albedo layer is elided)
-# dram__bytes_read.sum + dram__bytes_write.sum of k_trace per traced ray, from the ncu --set full capture of
-# one whole wave in profiles/r01d_ncu_full_trace_coop_selected.csv (17.58 GB over its nine k_trace_coop
-# launches, 216 M rays; same figure as the r01b capture of the per-lane kernel)
-TRACE_DRAM_BYTES_PER_RAY_NCU = 81.3
+# dram__bytes_read.sum + dram__bytes_write.sum of k_trace_coop per traced ray, from the ncu --set full capture of
+# one whole wave in profiles/r01f_ncu_full_wave_selected.csv (14.59 GB over its nine k_trace_coop launches,
+# 216.3 M rays; 17.58 GB = 81.3 B/ray before the path state became queue-ordered)
+TRACE_DRAM_BYTES_PER_RAY_NCU = 67.5
 
 
 def measured_peaks():
@@ -468,12 +468,12 @@ def main():
                          "traffic": (TRACE_DRAM_BYTES_PER_RAY_NCU * rays / world / n_ext_launches
                                      if kind == "cbox" and n_ext_launches else None),
                          "algorithmic_bytes_per_launch": trace_bytes / n_ext_launches if n_ext_launches else None,
-                         "traffic_source": "ncu DRAM bytes per traced ray (profiles/r01d, cbox) x rays per launch",
+                         "traffic_source": "ncu DRAM bytes per traced ray (profiles/r01f, cbox) x rays per launch",
                          "peak_source": peak_src,
                          # what actually bounds traversal on a cache-resident scene (SURVEY 8d caveat): cycles with an
                          # instruction issued / lanes per instruction, from the same ncu capture (not measured live)
-                         "issue_active_pct_ncu": 70.5 if kind == "cbox" else None,
-                         "lanes_per_instruction_ncu": 21.1 if kind == "cbox" else None,
+                         "issue_active_pct_ncu": 74.2 if kind == "cbox" else None,
+                         "lanes_per_instruction_ncu": 21.2 if kind == "cbox" else None,
                          "bytes_per_ray": {"extension": EXTEND_BYTES_PER_RAY, "shadow": SHADOW_BYTES_PER_RAY},
                          "launches": n_ext_launches,
                          "avg_launch_ms": ext_ms / n_ext_launches if n_ext_launches else None,
