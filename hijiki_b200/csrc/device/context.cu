@@ -392,7 +392,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       if (b == last) break;
       {
         KernelTimer t(c, stats, HJK_K_SHADE);
-        k_shade<<<g_tile, kTileThreads, 0, c->stream>>>(w, b);
+        k_shade<<<g_tile, kShadeThreads, 0, c->stream>>>(w, b);
       }
       launches++;
       if (b + 1 < last && (b + 1) % check_every == 0) {
@@ -608,7 +608,7 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   c->blocks_coop[0] = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<true>, kTravThreads, 0);
   c->blocks_coop[1] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kTileThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kShadeThreads, 0);
   c->blocks_tile = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
   c->blocks_light = std::max(occ, 1);

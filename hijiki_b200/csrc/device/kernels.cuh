@@ -86,9 +86,13 @@ constexpr int kPostponeLanes = 8;    // postpone primitive tests that fewer lane
 #ifndef HJK_TILE_THREADS
 #define HJK_TILE_THREADS 256
 #endif
-constexpr int kTileThreads = HJK_TILE_THREADS;
+constexpr int kTileThreads = HJK_TILE_THREADS;  // k_raygen
+#ifndef HJK_SHADE_THREADS
+#define HJK_SHADE_THREADS 128  // measured 64 / 128 / 256 / 512: k_shade 12.6 / 12.9 / 13.3 / 14.5 ms per step on cbox (64 loses on the sphere lattice)
+#endif
+constexpr int kShadeThreads = HJK_SHADE_THREADS;  // k_shade: tile of the extension queue sorted and shaded by one CTA
 #ifndef HJK_SHADE_MIN_BLOCKS
-#define HJK_SHADE_MIN_BLOCKS (1024 / HJK_TILE_THREADS)
+#define HJK_SHADE_MIN_BLOCKS (1024 / HJK_SHADE_THREADS)
 #endif
 
 // ---------------------------------------------------------------- block-level compaction
@@ -96,7 +100,7 @@ constexpr int kTileThreads = HJK_TILE_THREADS;
 // of the thread's element in the queue whose length lives at *counter.  One atomic per block.
 template <int NQ>
 struct BlockAppend {
-  uint32_t warp_total[NQ][kTileThreads / 32];
+  uint32_t warp_total[NQ][(kTileThreads > kShadeThreads ? kTileThreads : kShadeThreads) / 32];
   uint32_t base[NQ];
 };
 // TRAILING_SYNC = false when the caller passes at least one other block barrier before it calls
@@ -511,11 +515,11 @@ __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const
 // one bounce-loop iteration per hit and appends the next extension ray and the shadow ray to
 // their queues by block-level compaction.
 struct TileSort {
-  uint32_t warp_count[5][kTileThreads / 32];
+  uint32_t warp_count[5][kShadeThreads / 32];
   uint32_t n_hits;
-  uint32_t entry[kTileThreads];
-  uint32_t src[kTileThreads];  // position in the tile before the sort (the path state is read from there)
-  f4 hit[kTileThreads];
+  uint32_t entry[kShadeThreads];
+  uint32_t src[kShadeThreads];  // position in the tile before the sort (the path state is read from there)
+  f4 hit[kShadeThreads];
 };
 
 // Front part of a tile: the thread's queue entry, its hit record and material tag (0xFFFFFFFF = miss or
@@ -523,7 +527,7 @@ struct TileSort {
 // loads travel while that tile waits for its append atomics.
 __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_t* q, uint32_t n, uint32_t tile,
                                                  uint32_t bounce, uint32_t& entry, f4& h, uint32_t& tag) {
-  const uint32_t i = tile * kTileThreads + threadIdx.x;
+  const uint32_t i = tile * kShadeThreads + threadIdx.x;
   entry = 0, tag = 0xFFFFFFFFu;
   h = F4(0.f, 0.f, 0.f, 0.f);
   if (i < n) {
@@ -533,7 +537,7 @@ __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_
     if (id >= 0) tag = ld4(w.scene.materials + id) >> HJK_MATERIAL_TAG_SHIFT;
   }
   // start the tile after this one towards L1
-  const uint32_t i_next = i + gridDim.x * kTileThreads;
+  const uint32_t i_next = i + gridDim.x * kShadeThreads;
   if (i_next < n) {
     if ((threadIdx.x & 7u) == 0) prefetch_l1(q + i_next);  // 8 entries per 32-byte sector
     if ((threadIdx.x & 1u) == 0) {
@@ -544,7 +548,7 @@ __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads, HJK_SHADE_MIN_BLOCKS) k_shade(WaveDev w, uint32_t bounce) {
+__global__ void __launch_bounds__(kShadeThreads, HJK_SHADE_MIN_BLOCKS) k_shade(WaveDev w, uint32_t bounce) {
   __shared__ BlockAppend<2> sm;
   __shared__ TileSort ts;
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(kTileThreads, HJK_SHADE_MIN_BLOCKS) k_shade(Wa
   const uint32_t* q = w.ext_q[bounce & 1u];
   uint32_t* next_q = w.ext_q[(bounce + 1u) & 1u];
   uint32_t* const counter[2] = {ctr + CTR_STRIDE + CTR_EXT, ctr + CTR_SHADOW};
-  const uint32_t n_tiles = (n + kTileThreads - 1) / kTileThreads;
+  const uint32_t n_tiles = (n + kShadeThreads - 1) / kShadeThreads;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, par = bounce & 1u;
   uint32_t entry = 0, tag = 0xFFFFFFFFu;
   f4 h = F4(0.f, 0.f, 0.f, 0.f);
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(kTileThreads, HJK_SHADE_MIN_BLOCKS) k_shade(Wa
     if (threadIdx.x == 0) {  // exclusive scan of the 5 x 8 warp counts, tag-major
       uint32_t total = 0;
       for (uint32_t t = 0; t < 5; t++) {
-        for (uint32_t wi = 0; wi < kTileThreads / 32; wi++) {
+        for (uint32_t wi = 0; wi < kShadeThreads / 32; wi++) {
           const uint32_t c = ts.warp_count[t][wi];
           ts.warp_count[t][wi] = total;
           total += c;
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(kTileThreads, HJK_SHADE_MIN_BLOCKS) k_shade(Wa
     if (threadIdx.x < n_hits) {
       entry = ts.entry[threadIdx.x];
       slot = entry & 0x7FFFFFFFu;
-      const uint32_t e = tile * kTileThreads + ts.src[threadIdx.x];
+      const uint32_t e = tile * kShadeThreads + ts.src[threadIdx.x];
       VertexIn in;
       in.ray_o = w.ray_o[par][e];
       in.ray_d = w.ray_d[par][e];
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(kTileThreads, HJK_SHADE_MIN_BLOCKS) k_shade(Wa
     __syncthreads();
     if (threadIdx.x < 2) {
       uint32_t total = 0;
-      for (uint32_t wi = 0; wi < kTileThreads / 32; wi++) {
+      for (uint32_t wi = 0; wi < kShadeThreads / 32; wi++) {
         const uint32_t c = sm.warp_total[threadIdx.x][wi];
         sm.warp_total[threadIdx.x][wi] = total;
         total += c;
