@@ -463,3 +463,30 @@ def test_trace_kernel_variants_match_oracle(gpu_ctx, kind, max_bounces, use_bvh,
     assert st.n_paths == ost.n_paths
     assert diff.sum() <= 25 * 4
     assert abs(st.n_extension_rays - ost.n_extension_rays) <= 100
+
+
+@pytest.mark.parametrize("w,h,spp,max_bounces,rr_start", [
+    (1, 1, 3, 8, 3),        # a single texel
+    (7, 5, 2, 2, 3),        # a frame smaller than the 32x8 reconstruction tile
+    (40, 33, 2, 1, 3),      # one bounce: next-event estimation once
+    (65, 64, 2, 12, 0),     # roulette from the first bounce; one texel column spills into a second block
+    (64, 130, 1, 6, 100),   # roulette never starts within the bounce limit
+])
+def test_render_edge_shapes_match_oracle(gpu_ctx, w, h, spp, max_bounces, rr_start):
+    """Frame and parameter corner cases through hjk_render against the oracle (exact-tie mode: bit-identical)."""
+    compiled = _compiled("cbox_spheres")
+    gpu_ctx.scene_upload(compiled)
+    bs = 64
+    blocks = hj.ImageBlockGenerator(w, h, bs, spp).blocks()
+    gpu_ctx.frame_begin(w, h)
+    st = gpu_ctx.render(blocks, hj.make_params(max_bounces=max_bounces, rr_start=rr_start, flags=hj.HJK_RENDER_EXACT_TIES))
+    acc_g = gpu_ctx.readback(normalise=False)
+    O = _libs.oracle()
+    acc_o = np.zeros((h, w, 4), np.float32)
+    ost = _libs.OrcStats()
+    op = _libs.orc_params(max_bounces=max_bounces, rr_start=rr_start, use_bvh=0, block_size=bs)
+    assert O.orc_render(C.byref(compiled.view), _libs.ptr(blocks), blocks.size, C.byref(op), _libs.ptr(acc_o),
+                        C.byref(ost), 0) == 0
+    assert (st.n_paths, st.n_extension_rays, st.n_shadow_rays) == (ost.n_paths, ost.n_extension_rays, ost.n_shadow_rays)
+    diff = (acc_o.view(np.uint32) != acc_g.view(np.uint32)).any(axis=2)
+    assert diff.sum() <= 25 * gpu_ctx.get_info("unresolved_ties")
