@@ -99,7 +99,7 @@ struct HjkContext {
   int blocks_light = 0;                  // ... of the light tile kernels (raygen, bin)
   std::string error;
   bool profiling = false;
-  uint64_t wave_paths = 32u << 20;  // target camera paths per wave (4.9 GB of path state; tails amortise)
+  uint64_t wave_paths = 64u << 20;  // target camera paths per wave (13 GB of path state; tails amortise)
   float bvh_pad_rel = kDefaultBvhPadRel;
   int coop_trace = 1;    // 1 = k_trace_coop: pooled primitive tests (default mode only); 0 = per-lane k_trace
   uint32_t coop_batch_cost = 180;

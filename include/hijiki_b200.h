@@ -303,7 +303,7 @@ HJK_API int hjk_set_stream(HjkContext* ctx, void* cuda_stream);
 /* ----------------------------------------------------- misc / profiling */
 HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-event timing */
 /* Tuning options (all have measured defaults; none changes results):
- *   "wave_paths"             camera paths rendered per wave (default 32 Mi)
+ *   "wave_paths"             camera paths rendered per wave (default 64 Mi = 13 GB of path state)
  *   "bvh_builder"            0 = host SAH builder (default), 1 = GPU LBVH builder; next hjk_scene_upload
  *   "bvh_validate"           1 = run the host structural check on a GPU-built tree
  *   "bvh_pad_rel_e9"         outward pad of primitive boxes, in 1e-9 of the scene extent (default 10000)
