@@ -8,16 +8,20 @@
 //   3. SAH-optimal collapse of the binary tree into 8-wide nodes with <= 3 primitives per leaf
 //      (dynamic programme over "forest of at most i roots" costs, node cost 1, primitive 0.3);
 //   4. children assigned to slots so that slot ^ ray-octant gives a near-to-far order;
-//   5. child boxes quantised to 8 bits per plane, rounded outward, nodes emitted breadth-first
-//      (the children of a node are contiguous), primitives emitted in node order.
+//   5. child boxes quantised to 8 bits per plane, rounded outward; the children of a node are contiguous;
+//      the top of the tree is emitted breadth-first, each subtree below it into one contiguous run of
+//      nodes and primitives (steps 3 and 5 run on all host threads; the result does not depend on their number).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <limits>
+#include <memory>
 #include <thread>
+#include <vector>
 
 #include "wide_bvh_host.h"
 
@@ -28,6 +32,24 @@ constexpr float kInf = std::numeric_limits<float>::infinity();
 constexpr float kNodeCost = 1.0f;
 constexpr float kPrimCost = 0.3f;
 constexpr int kBins = 16;
+
+// Runs fn(i) for i in [0, n) on the host's threads (dynamic schedule; results must not depend on it).
+template <class Fn>
+void parallel_for(size_t n, Fn fn) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = std::min<size_t>(std::max(1u, std::min(hw, 32u)), n);
+  if (nt <= 1) {
+    for (size_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (size_t t = 0; t < nt; t++)
+    pool.emplace_back([&]() {
+      for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+    });
+  for (auto& th : pool) th.join();
+}
 
 struct Box {
   float lo[3], hi[3];
@@ -73,66 +95,141 @@ struct Binary {
 // into disjoint index ranges, and the result does not depend on the thread count.
 struct BinaryBuilder {
   const std::vector<Box>& boxes;
-  std::vector<float> cen;
   Binary& out;
+
+  // Occupied bins only: a node over c primitives touches at most c bins per axis, and most of the 2n-1
+  // nodes are tiny, so nothing here costs O(kBins) per node (no reset, no sweep over empty bins).
+  struct Bins {
+    Box bb[3][kBins];
+    uint32_t bc[3][kBins];
+    uint32_t mask[3];
+    void reset() { mask[0] = mask[1] = mask[2] = 0; }
+    void add(int a, int b, const Box& box) {
+      if ((mask[a] >> b) & 1u) {
+        bb[a][b].grow(box);
+        bc[a][b]++;
+      } else {
+        bb[a][b] = box;
+        bc[a][b] = 1;
+        mask[a] |= 1u << b;
+      }
+    }
+    void merge(const Bins& o) {
+      for (int a = 0; a < 3; a++)
+        for (uint32_t m = o.mask[a]; m; m &= m - 1) {
+          const int b = __builtin_ctz(m);
+          if ((mask[a] >> b) & 1u) {
+            bb[a][b].grow(o.bb[a][b]);
+            bc[a][b] += o.bc[a][b];
+          } else {
+            bb[a][b] = o.bb[a][b];
+            bc[a][b] = o.bc[a][b];
+            mask[a] |= 1u << b;
+          }
+        }
+    }
+  };
+  // Nodes over at least this many primitives spread their two passes over the host's threads (min / max
+  // and counts: the result does not depend on the chunking).
+  static constexpr uint32_t kParallelNode = 1u << 20, kChunk = 1u << 16;
 
   // Fills node `ni` (first/count already set); returns false for a leaf, else sets its children.
   bool split(uint32_t ni) {
     const uint32_t first = out.nodes[ni].first, count = out.nodes[ni].count;
     uint32_t* idx = out.order.data() + first;
+    // pass 1: bounds of the boxes and of the centroids
     Box nb, cb;
     nb.reset();
     cb.reset();
-    for (uint32_t i = 0; i < count; i++) {
-      nb.grow(boxes[idx[i]]);
-      cb.grow(&cen[(size_t)idx[i] * 3]);
+    auto bounds = [&](uint32_t i0, uint32_t i1, Box& nbox, Box& cbox) {
+      for (uint32_t i = i0; i < i1; i++) {
+        const Box& pb = boxes[idx[i]];
+        const float pc[3] = {0.5f * (pb.lo[0] + pb.hi[0]), 0.5f * (pb.lo[1] + pb.hi[1]), 0.5f * (pb.lo[2] + pb.hi[2])};
+        nbox.grow(pb);
+        cbox.grow(pc);
+      }
+    };
+    const uint32_t n_chunks = (count + kChunk - 1) / kChunk;
+    if (count >= kParallelNode) {
+      std::vector<Box> part(2 * (size_t)n_chunks);
+      parallel_for(n_chunks, [&](size_t c) {
+        part[2 * c].reset(), part[2 * c + 1].reset();
+        bounds((uint32_t)c * kChunk, std::min(count, ((uint32_t)c + 1) * kChunk), part[2 * c], part[2 * c + 1]);
+      });
+      for (uint32_t c = 0; c < n_chunks; c++) nb.grow(part[2 * c]), cb.grow(part[2 * c + 1]);
+    } else {
+      bounds(0, count, nb, cb);
     }
     out.nodes[ni].box = nb;
     if (count == 1) {
       out.nodes[ni].leaf = true;
       return false;
     }
-    // binned SAH over the three axes
+    // pass 2: binned SAH over the three axes, all three binned in one sweep over the primitives
+    float c0[3], scale[3];
+    bool usable[3];
+    for (int axis = 0; axis < 3; axis++) {
+      c0[axis] = cb.lo[axis];
+      const float ext = cb.hi[axis] - cb.lo[axis];
+      usable[axis] = ext > 0.f;
+      scale[axis] = usable[axis] ? (float)kBins / ext : 0.f;
+    }
+    auto fill = [&](uint32_t i0, uint32_t i1, Bins& bins) {
+      for (uint32_t i = i0; i < i1; i++) {
+        const Box& pb = boxes[idx[i]];
+        const float pc[3] = {0.5f * (pb.lo[0] + pb.hi[0]), 0.5f * (pb.lo[1] + pb.hi[1]), 0.5f * (pb.lo[2] + pb.hi[2])};
+        for (int axis = 0; axis < 3; axis++) {
+          if (!usable[axis]) continue;
+          int b = (int)((pc[axis] - c0[axis]) * scale[axis]);
+          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+          bins.add(axis, b, pb);
+        }
+      }
+    };
+    Bins bins;
+    bins.reset();
+    if (count >= kParallelNode) {
+      std::vector<Bins> part(n_chunks);
+      parallel_for(n_chunks, [&](size_t c) {
+        part[c].reset();
+        fill((uint32_t)c * kChunk, std::min(count, ((uint32_t)c + 1) * kChunk), part[c]);
+      });
+      for (uint32_t c = 0; c < n_chunks; c++) bins.merge(part[c]);
+    } else {
+      fill(0, count, bins);
+    }
+    // A split after bin b puts bins <= b left and bins > b right.  Splits after an empty bin cost the same
+    // as the split after the occupied bin below it and never win the strict comparison, so only occupied
+    // bins are visited (same winner as a sweep over all kBins - 1 splits, axis 0 first, lowest bin first).
     int best_axis = -1, best_split = -1;
     float best_cost = kInf;
     for (int axis = 0; axis < 3; axis++) {
-      const float c0 = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
-      if (!(ext > 0.f)) continue;
-      const float scale = (float)kBins / ext;
-      Box bb[kBins];
-      uint32_t bc[kBins];
-      for (int b = 0; b < kBins; b++) {
-        bb[b].reset();
-        bc[b] = 0;
-      }
-      for (uint32_t i = 0; i < count; i++) {
-        int b = (int)((cen[(size_t)idx[i] * 3 + axis] - c0) * scale);
-        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-        bb[b].grow(boxes[idx[i]]);
-        bc[b]++;
-      }
-      float right_area[kBins];
+      if (!usable[axis]) continue;
+      const Box* bb = bins.bb[axis];
+      const uint32_t* bc = bins.bc[axis];
+      int occ[kBins], n_occ = 0;
+      for (uint32_t m = bins.mask[axis]; m; m &= m - 1) occ[n_occ++] = __builtin_ctz(m);
+      float right_area[kBins];  // union of occupied bins occ[j..]
       uint32_t right_cnt[kBins];
       Box acc;
       acc.reset();
       uint32_t cnt = 0;
-      for (int b = kBins - 1; b > 0; b--) {
-        acc.grow(bb[b]);
-        cnt += bc[b];
-        right_area[b] = acc.half_area();
-        right_cnt[b] = cnt;
+      for (int j = n_occ - 1; j > 0; j--) {
+        acc.grow(bb[occ[j]]);
+        cnt += bc[occ[j]];
+        right_area[j] = acc.half_area();
+        right_cnt[j] = cnt;
       }
       acc.reset();
       cnt = 0;
-      for (int b = 0; b < kBins - 1; b++) {
-        acc.grow(bb[b]);
-        cnt += bc[b];
-        if (cnt == 0 || right_cnt[b + 1] == 0) continue;
-        float cost = acc.half_area() * (float)cnt + right_area[b + 1] * (float)right_cnt[b + 1];
+      for (int j = 0; j + 1 < n_occ; j++) {
+        acc.grow(bb[occ[j]]);
+        cnt += bc[occ[j]];
+        float cost = acc.half_area() * (float)cnt + right_area[j + 1] * (float)right_cnt[j + 1];
         if (cost < best_cost) {
           best_cost = cost;
           best_axis = axis;
-          best_split = b;
+          best_split = occ[j];
         }
       }
     }
@@ -140,9 +237,10 @@ struct BinaryBuilder {
     if (best_axis < 0) {
       mid = count / 2;  // coincident centroids: split the list in half
     } else {
-      const float c0 = cb.lo[best_axis], scale = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+      const float pc0 = c0[best_axis], pscale = scale[best_axis];
       uint32_t* m = std::partition(idx, idx + count, [&](uint32_t p) {
-        int b = (int)((cen[(size_t)p * 3 + best_axis] - c0) * scale);
+        const float pc = 0.5f * (boxes[p].lo[best_axis] + boxes[p].hi[best_axis]);
+        int b = (int)((pc - pc0) * pscale);
         b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
         return b <= best_split;
       });
@@ -188,9 +286,7 @@ void build_binary(const std::vector<Box>& boxes, Binary& out) {
   const uint32_t n = (uint32_t)boxes.size();
   out.order.resize(n);
   for (uint32_t i = 0; i < n; i++) out.order[i] = i;
-  BinaryBuilder bb{boxes, std::vector<float>((size_t)n * 3), out};
-  for (uint32_t i = 0; i < n; i++)
-    for (int k = 0; k < 3; k++) bb.cen[(size_t)i * 3 + k] = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
+  BinaryBuilder bb{boxes, out};
   out.nodes.assign((size_t)2 * n - 1, Node2());
   out.nodes[0].first = 0;
   out.nodes[0].count = n;
@@ -199,20 +295,19 @@ void build_binary(const std::vector<Box>& boxes, Binary& out) {
 
 // Dynamic programme of the wide-tree collapse.  cost[n][i-1] = cheapest way to represent the
 // subtree of binary node n as a forest of at most i wide-tree children (i = 1..7).
-struct Collapse {
-  std::vector<float> cost;      // 7 per node
-  std::vector<uint8_t> choice;  // 7 per node: i = 1: 0 leaf / 1 inner; i >= 2: k = roots given to
-                                // the left child, 0 = "same as i-1"
-  std::vector<uint8_t> root8;   // per node: left share when the node becomes an inner wide node
+struct Collapse {  // plain arrays: every entry is written by the sweep, first touched by the thread that fills it
+  std::unique_ptr<float[]> cost;      // 7 per node
+  std::unique_ptr<uint8_t[]> choice;  // 7 per node: i = 1: 0 leaf / 1 inner; i >= 2: k = roots given to
+                                      // the left child, 0 = "same as i-1"
+  std::unique_ptr<uint8_t[]> root8;   // per node: left share when the node becomes an inner wide node
 };
 
 void collapse_costs(const Binary& bin, Collapse& c) {
   const size_t n = bin.nodes.size();
-  c.cost.assign(n * 7, kInf);
-  c.choice.assign(n * 7, 0);
-  c.root8.assign(n, 0);
-  // children have larger indices than their parent (build order), so a reverse sweep is bottom-up
-  for (size_t ni = n; ni-- > 0;) {
+  c.cost.reset(new float[n * 7]);
+  c.choice.reset(new uint8_t[n * 7]);
+  c.root8.reset(new uint8_t[n]);
+  auto process = [&](size_t ni) {
     const Node2& nd = bin.nodes[ni];
     const float area = nd.box.half_area();
     float* cn = &c.cost[ni * 7];
@@ -222,7 +317,8 @@ void collapse_costs(const Binary& bin, Collapse& c) {
         cn[i] = area * kPrimCost;
         ch[i] = 0;
       }
-      continue;
+      c.root8[ni] = 0;
+      return;
     }
     const float* cl = &c.cost[(size_t)nd.left * 7];
     const float* cr = &c.cost[(size_t)nd.right * 7];
@@ -260,7 +356,31 @@ void collapse_costs(const Binary& bin, Collapse& c) {
         ch[i - 1] = 0;
       }
     }
+  };
+  // Preorder numbering: the subtree over `count` primitives rooted at r owns nodes [r, r + 2 count - 1),
+  // children after their parent.  Subtrees below ~n/256 primitives are swept bottom-up by independent
+  // threads, the few nodes above them afterwards.
+  const uint32_t n_prims = bin.nodes[0].count;
+  const uint32_t task_prims = std::max<uint32_t>(4096u, n_prims / 256u);
+  std::vector<uint32_t> top, roots, stack{0};
+  while (!stack.empty()) {
+    const uint32_t ni = stack.back();
+    stack.pop_back();
+    const Node2& nd = bin.nodes[ni];
+    if (nd.leaf || nd.count <= task_prims) {
+      roots.push_back(ni);
+    } else {
+      top.push_back(ni);
+      stack.push_back(nd.left);
+      stack.push_back(nd.right);
+    }
   }
+  parallel_for(roots.size(), [&](size_t t) {
+    const size_t r = roots[t], end = r + 2 * (size_t)bin.nodes[r].count - 1;
+    for (size_t ni = end; ni-- > r;) process(ni);
+  });
+  std::sort(top.begin(), top.end());
+  for (size_t i = top.size(); i-- > 0;) process(top[i]);
 }
 
 struct ChildRef {
@@ -458,19 +578,16 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
   lap("collapse costs");
   out.sah_cost = col.cost[0] / std::max(bin.nodes[0].box.half_area(), 1e-30f);
 
-  // breadth-first emission
+  // Emission.  One wide node at a time: gather its (at most 8) children from the collapse choices,
+  // assign slots, quantise, append its primitives and reserve the contiguous block of its inner children.
+  // `nodes` / `prims` / `queue` are the arrays being appended to (the top of the tree, or one subtree's arena).
   struct Pending {
     uint32_t node2;  // binary node whose subtree this wide node covers
-    uint32_t wide;   // index in out.nodes
+    uint32_t wide;   // index in `nodes`
     uint32_t depth;
   };
-  std::vector<Pending> queue;
-  out.nodes.emplace_back();
-  queue.push_back({0, 0, 1});
-  std::vector<ChildRef> kids;
-  for (size_t qi = 0; qi < queue.size(); qi++) {
-    const Pending cur = queue[qi];
-    out.depth = std::max(out.depth, cur.depth);
+  auto emit_one = [&](const Pending cur, std::vector<WideNode>& nodes, std::vector<WidePrim>& prims,
+                      std::vector<Pending>& queue, std::vector<ChildRef>& kids) -> bool {
     const Node2& nd = bin.nodes[cur.node2];
     kids.clear();
     if (nd.leaf) {
@@ -528,14 +645,13 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
       e = std::max(e, -126);
       while (std::ceil(extent / std::ldexp(1.0, e)) > 255.0) e++;
       if (e > 127) {
-        err = "scene extent too large to quantise";
         return false;
       }
       wn.e[k] = (uint8_t)(e + 127);
       scale[k] = std::ldexp(1.0, e);
     }
-    wn.child_base = (uint32_t)out.nodes.size();
-    wn.prim_base = (uint32_t)out.prims.size();
+    wn.child_base = (uint32_t)nodes.size();
+    wn.prim_base = (uint32_t)prims.size();
     uint32_t prim_off = 0, n_inner = 0;
     for (int sl = 0; sl < 8; sl++) {
       const int c = child_in_slot[sl];
@@ -561,7 +677,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
         for (uint32_t i = 0; i < cnt; i++) {
           WidePrim wp;
           make_prim(s, bin.order[cn.first + i], wp);
-          out.prims.push_back(wp);
+          prims.push_back(wp);
         }
         prim_off += cnt;
       } else {
@@ -574,12 +690,75 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
     for (int sl = 0; sl < 8; sl++) {
       const int c = child_in_slot[sl];
       if (c < 0 || kids[c].leaf) continue;
-      queue.push_back({kids[c].node2, (uint32_t)out.nodes.size(), cur.depth + 1});
-      out.nodes.emplace_back();
+      queue.push_back({kids[c].node2, (uint32_t)nodes.size(), cur.depth + 1});
+      nodes.emplace_back();
     }
     (void)n_inner;
-    out.nodes[cur.wide] = wn;
+    nodes[cur.wide] = wn;
+      return true;
+  };
+
+  // The top of the tree is emitted breadth-first by one thread until enough subtrees are pending; each of
+  // those is then emitted into its own arena by the host's threads, and the arenas are appended in task
+  // order (indices rebased), so the layout does not depend on the thread count.
+  std::vector<Pending> queue;
+  std::vector<ChildRef> kids;
+  out.nodes.emplace_back();
+  queue.push_back({0, 0, 1});
+  size_t qi = 0;
+  const size_t want_tasks = 2048;
+  for (; qi < queue.size() && queue.size() - qi < want_tasks; qi++) {
+    out.depth = std::max(out.depth, queue[qi].depth);
+    if (!emit_one(queue[qi], out.nodes, out.prims, queue, kids)) {
+      err = "scene extent too large to quantise";
+      return false;
+    }
   }
+  struct Arena {
+    std::vector<WideNode> nodes;  // [0] = the task's root (it lives at Pending::wide of the top array)
+    std::vector<WidePrim> prims;
+    uint32_t depth = 0;
+    bool ok = true;
+  };
+  const size_t n_tasks = queue.size() - qi;
+  std::vector<Arena> arenas(n_tasks);
+  parallel_for(n_tasks, [&](size_t t) {
+    Arena& ar = arenas[t];
+    std::vector<Pending> q;
+    std::vector<ChildRef> k;
+    ar.nodes.emplace_back();
+    q.push_back({queue[qi + t].node2, 0, queue[qi + t].depth});
+    for (size_t i = 0; i < q.size() && ar.ok; i++) {
+      ar.depth = std::max(ar.depth, q[i].depth);
+      ar.ok = emit_one(q[i], ar.nodes, ar.prims, q, k);
+    }
+  });
+  std::vector<uint32_t> node_off(n_tasks + 1), prim_off(n_tasks + 1);
+  node_off[0] = (uint32_t)out.nodes.size(), prim_off[0] = (uint32_t)out.prims.size();
+  for (size_t t = 0; t < n_tasks; t++) {
+    if (!arenas[t].ok) {
+      err = "scene extent too large to quantise";
+      return false;
+    }
+    out.depth = std::max(out.depth, arenas[t].depth);
+    node_off[t + 1] = node_off[t] + (uint32_t)arenas[t].nodes.size() - 1u;
+    prim_off[t + 1] = prim_off[t] + (uint32_t)arenas[t].prims.size();
+  }
+  out.nodes.resize(node_off[n_tasks]);
+  out.prims.resize(prim_off[n_tasks]);
+  parallel_for(n_tasks, [&](size_t t) {
+    Arena& ar = arenas[t];
+    // arena node i >= 1 moves to node_off + i - 1, arena primitive j to prim_off + j
+    for (WideNode& wn : ar.nodes) {
+      wn.child_base = node_off[t] + wn.child_base - 1u;
+      wn.prim_base += prim_off[t];
+    }
+    out.nodes[queue[qi + t].wide] = ar.nodes[0];
+    std::copy(ar.nodes.begin() + 1, ar.nodes.end(), out.nodes.begin() + node_off[t]);
+    std::copy(ar.prims.begin(), ar.prims.end(), out.prims.begin() + prim_off[t]);
+    std::vector<WideNode>().swap(ar.nodes);
+    std::vector<WidePrim>().swap(ar.prims);
+  });
   lap("emit wide nodes");
   out.n_shapes = n;
   sphere_guard_bounds(s, out);
