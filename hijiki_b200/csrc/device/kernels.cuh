@@ -2,16 +2,20 @@
 // render.glsl megakernel (reference shader/render.glsl:149-175) and of its per-block
 // reconstruction dispatch (shader/reconstruction.glsl:22-66).
 //
-//   k_raygen    one thread per path slot: RNG seed, camera ray, layer initialisation
-//   k_trace     persistent warps pull the extension rays of bounce b (closest hit = "extend") and
-//               the shadow rays of bounce b-1 (any hit) from one work range and walk the 8-wide
-//               BVH, short stack in shared memory
-//   k_shade     per tile of the queue: misses dropped, hits counting-sorted by material tag in
-//               shared memory (ballot / prefix sum), then emission, next-event estimation, BSDF
-//               sample, roulette; the next extension ray and the shadow ray are appended to their
-//               queues by block-level compaction
-//   k_recon     shared-memory tiled bilateral splat of one or more passes into the accumulator
+//   k_raygen      one thread per path slot: RNG seed, camera ray, layer initialisation
+//   k_trace_coop  persistent warps pull the extension rays of bounce b (closest hit = "extend") and
+//                 the shadow rays of bounce b-1 (any hit) from one work range and walk the 8-wide
+//                 BVH, short stack in shared memory; the primitive tests of a warp are pooled over
+//                 its 32 lanes when the per-lane counts are skewed (the default trace kernel)
+//   k_trace       the same with a per-lane primitive loop: exact-tie mode, hjk_trace_first_hit
+//   k_shade       per tile of the queue: misses dropped, hits counting-sorted by material tag in
+//                 shared memory (ballot / prefix sum), then emission, next-event estimation, BSDF
+//                 sample, roulette; the surviving path and its shadow ray are appended to their
+//                 queues by block-level compaction
+//   k_recon       shared-memory tiled bilateral splat of one or more passes into the accumulator
 //
+// Path state (ray, throughput, RNG) and hit records are QUEUE-ORDERED: element e belongs to the
+// path at position e of the bounce's extension queue, so every stream a kernel touches is dense.
 // No host synchronisation inside a wave: every kernel reads its element count from device
 // counters written by the previous stage.
 #pragma once
