@@ -125,6 +125,7 @@ _SIGNATURES = {
                                               _P, C.c_uint64]),
     "hjk_host_write_exr": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32, C.c_uint64]),
     "hjk_host_bvh_stats": (C.c_int, [C.POINTER(HjkScene), C.c_float, _P]),
+    "hjk_host_bvh_digest": (C.c_int, [C.POINTER(HjkScene), C.c_float, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

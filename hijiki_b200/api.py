@@ -54,6 +54,12 @@ class CompiledScene:
         return {"nodes": int(out[0]), "prims": int(out[1]), "depth": int(out[2]), "valid": bool(out[3]),
                 "sah_cost": out[4] / 1000.0, "bytes": int(out[5])}
 
+    def bvh_digest(self, n_threads: int = 0, pad_rel: float = -1.0) -> int:
+        """FNV-1a of the wide BVH built on at most ``n_threads`` host threads (0 = all)."""
+        out = np.zeros(1, dtype=np.uint64)
+        _check_host(self._lib, self._lib.hjk_host_bvh_digest(C.byref(self.view), pad_rel, n_threads, as_ptr(out)))
+        return int(out[0])
+
     def close(self) -> None:
         if self._handle:
             self._lib.hjk_host_scene_free(self._handle)

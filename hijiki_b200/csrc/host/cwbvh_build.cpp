@@ -33,11 +33,17 @@ constexpr float kNodeCost = 1.0f;
 constexpr float kPrimCost = 0.3f;
 constexpr int kBins = 16;
 
+std::atomic<int> g_builder_threads{0};  // 0 = all
+unsigned builder_threads() {
+  const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  const int cap = g_builder_threads.load();
+  return cap > 0 ? std::min(hw, (unsigned)cap) : hw;
+}
+
 // Runs fn(i) for i in [0, n) on the host's threads (dynamic schedule; results must not depend on it).
 template <class Fn>
 void parallel_for(size_t n, Fn fn) {
-  const unsigned hw = std::thread::hardware_concurrency();
-  const size_t nt = std::min<size_t>(std::max(1u, std::min(hw, 32u)), n);
+  const size_t nt = std::min<size_t>(builder_threads(), n);
   if (nt <= 1) {
     for (size_t i = 0; i < n; i++) fn(i);
     return;
@@ -270,7 +276,7 @@ struct BinaryBuilder {
   }
 
   void build_parallel(uint32_t root, int depth) {
-    if (depth >= 5 || out.nodes[root].count < 65536u) {  // at most 32 concurrent subtrees
+    if (depth >= 5 || out.nodes[root].count < 65536u || builder_threads() == 1) {  // at most 32 concurrent subtrees
       build_serial(root);
       return;
     }
@@ -511,6 +517,8 @@ void sphere_guard_bounds(const HjkScene& s, WideBvh& out) {
   out.sph_rmin = rmin;
   out.sph_rmax = rmax;
 }
+
+void set_builder_threads(int n) { g_builder_threads.store(n < 0 ? 0 : n); }
 
 bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string& err) {
   out = WideBvh();

@@ -133,6 +133,37 @@ int hjk_host_bvh_stats(const HjkScene* scene, float pad_rel, uint64_t* out6) {
   }
 }
 
+int hjk_host_bvh_digest(const HjkScene* scene, float pad_rel, int n_threads, uint64_t* out_digest) {
+  if (!scene || !out_digest) {
+    g_host_error = "hjk_host_bvh_digest: null argument";
+    return HJK_ERR_INVALID_ARGUMENT;
+  }
+  try {
+    hjk::WideBvh bvh;
+    std::string err;
+    hjk::set_builder_threads(n_threads);
+    const bool built = hjk::build_wide_bvh(*scene, pad_rel < 0.f ? hjk::kDefaultBvhPadRel : pad_rel, bvh, err);
+    hjk::set_builder_threads(0);
+    if (!built) {
+      g_host_error = err;
+      return HJK_ERR_INVALID_ARGUMENT;
+    }
+    uint64_t h = 1469598103934665603ull;  // FNV-1a
+    auto eat = [&h](const void* p, size_t n) {
+      const unsigned char* b = static_cast<const unsigned char*>(p);
+      for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    eat(bvh.nodes.data(), bvh.nodes.size() * sizeof(hjk::WideNode));
+    eat(bvh.prims.data(), bvh.prims.size() * sizeof(hjk::WidePrim));
+    *out_digest = h;
+    return HJK_OK;
+  } catch (const std::exception& e) {
+    hjk::set_builder_threads(0);
+    g_host_error = e.what();
+    return HJK_ERR_OUT_OF_MEMORY;
+  }
+}
+
 int hjk_host_scene_free(HjkHostScene* hs) {
   delete hs;
   return HJK_OK;

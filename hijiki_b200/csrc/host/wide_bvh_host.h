@@ -25,6 +25,8 @@ struct WideBvh {
 constexpr float kDefaultBvhPadRel = 1e-5f;
 
 bool build_wide_bvh(const HjkScene& scene, float pad_rel, WideBvh& out, std::string& err);
+// cap on the host threads the builder uses (0 = all of them, the default)
+void set_builder_threads(int n);
 bool validate_wide_bvh(const HjkScene& scene, const WideBvh& bvh, std::string& err);
 void sphere_guard_bounds(const HjkScene& scene, WideBvh& out);
 

@@ -347,6 +347,10 @@ HJK_API const char* hjk_host_last_error(void);
  * passed (every shape reachable once, every box contains what is below it),
  * out[4] root SAH cost x 1000, out[5] bytes.  pad_rel < 0 selects the default pad. */
 HJK_API int hjk_host_bvh_stats(const HjkScene* scene, float pad_rel, uint64_t* out6);
+/* Same build on at most n_threads host threads (0 = all) and a 64-bit FNV-1a digest of the node and
+ * primitive-record bytes: the builder runs its phases on every host thread, and the tree must not depend
+ * on how many there are (checked by the tests with 1, 3 and all threads). */
+HJK_API int hjk_host_bvh_digest(const HjkScene* scene, float pad_rel, int n_threads, uint64_t* out_digest);
 
 /* ImageBlockGenerator (src/main.rs:619-682) with the OS-entropy draws replaced
  * by a recorded splitmix64 stream from `root_seed`.  Returns the block count

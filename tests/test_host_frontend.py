@@ -106,6 +106,15 @@ def test_wide_bvh_is_structurally_valid(kind):
     assert st["bytes"] == st["nodes"] * 80 + st["prims"] * 48
 
 
+def test_wide_bvh_does_not_depend_on_the_thread_count():
+    """The host builder runs its SAH binning, collapse sweep and emission on every host thread; nodes and
+    primitive records must come out bit-identical on 1, 3 and all threads (1.16 M triangles: large enough for
+    the all-threads binning of nodes over 2^20 primitives, the per-subtree sweeps and the emission arenas)."""
+    for scene in (hj.Scene.from_obj(_libs.CBOX_OBJ).compile(), hj.Scene.terrain(760).compile()):
+        digests = {scene.bvh_digest(n) for n in (1, 3, 0)}
+        assert len(digests) == 1, digests
+
+
 def test_synthetic_scene_shapes():
     sp = hj.Scene.spheres(8).compile()
     assert sp.info.num_spheres == 512 and sp.info.num_triangles == 4 and sp.info.num_emitters == 2
