@@ -456,7 +456,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": label, "spp_per_step_per_gpu": sps, "blocks_per_step_per_gpu": sps * bpp,
                        "parallelism": f"sample-pass dp{world}",
-                       "l2": "inputs larger than L2: the path state + queues of one wave (~0.7 GB) exceed the 126 MB L2",
+                       "l2": "inputs larger than L2: the path state + queues of one wave (~200 B per path, GBs per wave) exceed the 126 MB L2",
                        "image_mean": result_mean, "bvh": info,
                        "scene_build_s": round(t_scene, 2), "bvh_build_upload_s": round(t_upload, 2)},
             "rays": {"extension": ext_rays, "shadow": sh_rays,
