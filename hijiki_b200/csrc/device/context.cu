@@ -276,26 +276,38 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   const uint32_t n_passes = (uint32_t)plan.passes.size();
   uint32_t wave_passes = (uint32_t)std::max<uint64_t>(1, (c->wave_paths + n_pixels / 2) / n_pixels);
   wave_passes = std::min(wave_passes, n_passes);
-  const size_t n_slots = n_pixels * wave_passes;
-  if (n_slots > 0x7FFFFFFFull) return c->fail(HJK_ERR_UNSUPPORTED, "wave too large");
+  while ((size_t)n_pixels * wave_passes > 0x7FFFFFFFull && wave_passes > 1) wave_passes /= 2;
+  if (n_pixels * wave_passes > 0x7FFFFFFFull) return c->fail(HJK_ERR_UNSUPPORTED, "frame too large");
   const int R = (int)prm->recon_radius, taps = 2 * R + 1;
   const bool do_recon = !(prm->flags & HJK_RENDER_NO_RECON);
   if (do_recon && R > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
 
-  for (int par = 0; par < 2; par++) {  // queue-ordered path state, ping-pong by bounce parity
-    HJK_CUDA(c, c->d_ray_o[par].ensure(n_slots));
-    HJK_CUDA(c, c->d_ray_d[par].ensure(n_slots));
-    HJK_CUDA(c, c->d_thr[par].ensure(n_slots));
-    if (c->has_extinction) HJK_CUDA(c, c->d_ext[par].ensure(n_slots));
+  // Path state of one wave (~200 B per path slot).  If the device cannot hold the configured wave (other
+  // tenants, a smaller part), halve the wave until it fits: only launch shapes change, never results.
+  size_t n_slots = 0;
+  for (;;) {
+    n_slots = n_pixels * wave_passes;
+    cudaError_t e = cudaSuccess;
+    auto want = [&](DevBuf<f4>& b) {
+      if (e == cudaSuccess) e = b.ensure(n_slots);
+    };
+    for (int par = 0; par < 2; par++) {  // queue-ordered path state, ping-pong by bounce parity
+      want(c->d_ray_o[par]), want(c->d_ray_d[par]), want(c->d_thr[par]);
+      if (c->has_extinction) want(c->d_ext[par]);
+    }
+    want(c->d_hit), want(c->d_layer0), want(c->d_layer1), want(c->d_sh_o), want(c->d_sh_d), want(c->d_sh_c);
+    if (e == cudaSuccess) e = c->d_ext_q0.ensure(n_slots);
+    if (e == cudaSuccess) e = c->d_ext_q1.ensure(n_slots);
+    if (e == cudaSuccess) break;
+    if (e != cudaErrorMemoryAllocation || wave_passes == 1) HJK_CUDA(c, e);
+    cudaGetLastError();  // clear the allocation error, give back what was taken and retry with half the wave
+    for (int par = 0; par < 2; par++)
+      c->d_ray_o[par].release(), c->d_ray_d[par].release(), c->d_thr[par].release(), c->d_ext[par].release();
+    c->d_hit.release(), c->d_layer0.release(), c->d_layer1.release(), c->d_sh_o.release(), c->d_sh_d.release();
+    c->d_sh_c.release(), c->d_ext_q0.release(), c->d_ext_q1.release();
+    c->have_features = false;
+    wave_passes = (wave_passes + 1) / 2;
   }
-  HJK_CUDA(c, c->d_hit.ensure(n_slots));
-  HJK_CUDA(c, c->d_layer0.ensure(n_slots));
-  HJK_CUDA(c, c->d_layer1.ensure(n_slots));
-  HJK_CUDA(c, c->d_sh_o.ensure(n_slots));
-  HJK_CUDA(c, c->d_sh_d.ensure(n_slots));
-  HJK_CUDA(c, c->d_sh_c.ensure(n_slots));
-  HJK_CUDA(c, c->d_ext_q0.ensure(n_slots));
-  HJK_CUDA(c, c->d_ext_q1.ensure(n_slots));
   const size_t n_ctr = ((size_t)prm->max_bounces + 1) * CTR_STRIDE;
   HJK_CUDA(c, c->d_counters.ensure(n_ctr));
   HJK_CUDA(c, c->d_unresolved.ensure(1));
