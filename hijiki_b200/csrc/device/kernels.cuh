@@ -316,9 +316,9 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 // free — the owner's ray travels by shuffle, the nearest accepted hit comes back through a 64-bit
 // shared-memory atomicMin keyed by (t, testing lane).  In the per-lane loop the same tests ran at ~9
 // of 32 lanes (lanes of one warp reach leaves holding 0..24 primitives at the same step).
-// Closest hit = the candidate of smallest t under the ray's current interval, then tMax = t - M_EPS:
-// the same result as the sequential rule except inside clusters closer than M_EPS (ties).  The
-// exact-tie mode keeps the per-lane loop (it must record every candidate).
+// Closest hit = closer_hit (traverse.cuh): the candidate of smallest t, equal t by the lower shape id —
+// the same function of the hit set whether a primitive is tested by its own lane or by another one.
+// The exact-tie mode keeps the per-lane loop (it must record every candidate).
 template <bool GUARD, class IO>
 __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO& io, uint32_t n, uint32_t* cursor,
                                                     float eps, int fetch_threshold, uint32_t coop_batch_cost) {
@@ -390,11 +390,11 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
         const f4 r3 = r2;
 #endif
         float t, u, v;
-        if (intersect_prim(sc, s, r0, r1, r2, r3, t, u, v)) {
+        if (intersect_prim(sc, s, r0, r1, r2, r3, t, u, v) && closer_hit(s, t, __float_as_uint(r0.w))) {
           s.hit_id = (int32_t)__float_as_uint(r0.w);
           s.hit_t = t, s.hit_u = u, s.hit_v = v;
           if (s.slot >> 31) break;
-          s.tmax = x::sub(t, eps);  // scene.glsl:116
+          s.tmax = t;
         }
       }
     } else {
@@ -407,7 +407,11 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
       }
       const uint32_t total = sum_cnt;
       const uint32_t excl = incl - pooled;
+      // key = (t bits, low 27 bits of the shape id, testing lane): the minimum is the closest hit, equal t
+      // by the lower id (closer_hit); the lane bits only tell the owner where u, v and the full id are
       unsigned long long cur_key = ~0ull;
+      if (active && s.hit_id >= 0)
+        cur_key = ((unsigned long long)__float_as_uint(s.hit_t) << 32) | (((uint32_t)s.hit_id & 0x07FFFFFFu) << 5) | 31u;
       sm_best[threadIdx.x] = ~0ull;
       __syncwarp();
       for (uint32_t base = 0; base < total; base += 32u) {
@@ -442,7 +446,8 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
 #endif
           if (intersect_prim(sc, r, r0, r1, r2, r3, t, u, v)) {
             id = __float_as_uint(r0.w);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | lane;
+            const unsigned long long key =
+                ((unsigned long long)__float_as_uint(t) << 32) | ((id & 0x07FFFFFFu) << 5) | lane;
             atomicMin(&sm_best[(threadIdx.x & ~31u) + owner], key);
           }
         }
@@ -450,7 +455,7 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
         // owners pick up an improvement made by this batch; the winner's u, v, id come by shuffle
         unsigned long long key = cur_key;
         if (pooled) key = sm_best[threadIdx.x];
-        const bool improved = key < cur_key;
+        const bool improved = (key >> 5) < (cur_key >> 5);
         const int src = improved ? (int)(key & 31ull) : (int)lane;
         const float wu = __shfl_sync(FULL, u, src), wv = __shfl_sync(FULL, v, src);
         const uint32_t wid = __shfl_sync(FULL, id, src);
@@ -459,7 +464,7 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
           s.hit_id = (int32_t)wid;
           s.hit_t = __uint_as_float((uint32_t)(key >> 32));
           s.hit_u = wu, s.hit_v = wv;
-          s.tmax = x::sub(s.hit_t, eps);  // scene.glsl:116
+          s.tmax = s.hit_t;
         }
         __syncwarp();
       }

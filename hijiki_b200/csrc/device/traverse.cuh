@@ -3,10 +3,14 @@
 // restated with exact fp32 operation order so that accepted hits carry the same t/u/v bits
 // as the reference arithmetic.
 //
-// Closest hit keeps the reference's rule "after an accepted hit, tMax = t - M_EPS"
-// (scene.glsl:116), so primitives are accepted under the same interval test; only the
-// visiting order differs (near child first), which changes the winner only among hits
-// closer than M_EPS to each other (SURVEY §8-Q1 "ties").  Any hit returns as soon as one
+// Closest hit, default mode: the hit of smallest t the reference's interval test accepts, exactly
+// equal t resolved by the lower shape id (closer_hit below).  That is a function of the SET of
+// primitives the ray hits, not of the order they are visited in, so results do not depend on warp
+// composition, wave size or the tree.  The reference instead keeps "tMax = t - M_EPS after an
+// accepted hit" (scene.glsl:116) along its linear scan, which makes its winner order-dependent
+// among hits closer than M_EPS to each other (SURVEY §8-Q1 "ties"): outside such clusters both
+// rules give the same hit; inside them this one reports the nearest member, the exact-tie mode
+// (TieCands below) the member the reference's scan order picks.  Any hit returns as soon as one
 // primitive is accepted, which is exactly when the reference's shadow overload
 // (scene.glsl:92-96) returns true.
 //
@@ -185,6 +189,13 @@ HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4&
     }
   }
   return hitmask;
+}
+
+// Default-mode replacement rule of the closest hit (see the head of this file): strictly closer, or
+// exactly as far with a lower shape id.  After an accepted hit tmax = t, so intersect_prim's own
+// interval test already rejects everything farther.
+HJK_HD bool closer_hit(const TravState& s, float t, uint32_t id) {
+  return s.hit_id < 0 || t < s.hit_t || (t == s.hit_t && id < (uint32_t)s.hit_id);
 }
 
 // One primitive record against the ray, in the reference's exact arithmetic.
@@ -417,10 +428,10 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
             if (cands_full(cands)) cands.prune(s.t_cull);  // far-to-near visiting order leaves stale entries
             cands.add(t, x::as_uint(r0.w), prim_index);
           }
-        } else {
+        } else if (closer_hit(s, t, x::as_uint(r0.w))) {
           s.hit_id = (int32_t)x::as_uint(r0.w);
           s.hit_t = t, s.hit_u = u, s.hit_v = v;
-          s.tmax = x::sub(t, eps);  // scene.glsl:116
+          s.tmax = t;
         }
       }
     }

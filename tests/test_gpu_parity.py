@@ -490,3 +490,31 @@ def test_render_edge_shapes_match_oracle(gpu_ctx, w, h, spp, max_bounces, rr_sta
     assert (st.n_paths, st.n_extension_rays, st.n_shadow_rays) == (ost.n_paths, ost.n_extension_rays, ost.n_shadow_rays)
     diff = (acc_o.view(np.uint32) != acc_g.view(np.uint32)).any(axis=2)
     assert diff.sum() <= 25 * gpu_ctx.get_info("unresolved_ties")
+
+
+@pytest.mark.parametrize("kind,max_bounces", [("cbox_spheres", 12), ("spheres", 16)])
+def test_default_mode_is_order_independent(gpu_ctx, kind, max_bounces):
+    """The default closest-hit rule (smallest t, equal t by the lower shape id) is a function of the hit set:
+    pooled or per-lane primitive tests, one trace kernel or the other, small or large waves — same frame, bit
+    for bit, ties included."""
+    compiled = _compiled(kind)
+    gpu_ctx.scene_upload(compiled)
+    w, h, bs, spp = 136, 100, 64, 4
+    blocks = hj.ImageBlockGenerator(w, h, bs, spp).blocks()
+    frames, counts = [], []
+    try:
+        for coop, cost, wave in [(1, 180, 64 << 20), (1, 0, 64 << 20), (0, 180, 64 << 20), (1, 180, 20000), (1, 400, 64 << 20)]:
+            gpu_ctx.set_option("coop_trace", coop)
+            gpu_ctx.set_option("coop_batch_cost", cost)
+            gpu_ctx.set_option("wave_paths", wave)
+            gpu_ctx.frame_begin(w, h)
+            st = gpu_ctx.render(blocks, hj.make_params(max_bounces=max_bounces))
+            frames.append(gpu_ctx.readback(normalise=False))
+            counts.append((st.n_paths, st.n_extension_rays, st.n_shadow_rays))
+    finally:
+        gpu_ctx.set_option("coop_trace", 1)
+        gpu_ctx.set_option("coop_batch_cost", 180)
+        gpu_ctx.set_option("wave_paths", 64 << 20)
+    assert len(set(counts)) == 1, counts
+    for f in frames[1:]:
+        assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))

@@ -12,8 +12,8 @@ print(f"default wave: {st.mrays_per_s:.0f} Mrays/s, {st.n_launches} launches")
 ctx.set_option("wave_paths", 2**31 - 1)   # 512 passes of 1080p = 1.06 G slots = 212 GB: does not fit
 ctx.frame_begin(W, H); st = ctx.render(blocks, p); got = ctx.readback(normalise=False)
 diff = int((ref.view(np.uint32) != got.view(np.uint32)).any(axis=2).sum())
-print(f"oversized wave: {st.mrays_per_s:.0f} Mrays/s, {st.n_launches} launches, texels differing (ties resolve by warp "
-      f"composition in the default mode): {diff} of {W * H}")
+print(f"oversized wave: {st.mrays_per_s:.0f} Mrays/s, {st.n_launches} launches, texels differing from the default "
+      f"wave's frame (the closest-hit rule is order-independent: expect 0): {diff} of {W * H}")
 p = hj.make_params(max_bounces=8, flags=hj.HJK_RENDER_EXACT_TIES)
 frames = []
 for wave in (64 << 20, 2**31 - 1):
