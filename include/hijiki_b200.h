@@ -188,8 +188,10 @@ enum {
   HJK_RENDER_NO_RECON = 1u << 1,    /* integrate only (debug / feature export) */
   HJK_RENDER_KEEP_FEATURES = 1u << 2, /* keep the last pass' intermediate layers for hjk_read_intermediate */
   HJK_RENDER_EXACT_TIES = 1u << 3     /* resolve hits closer than eps to each other exactly as the reference's
-                                         linear scan does (scene.glsl:134-157) instead of near-child-first;
-                                         slower; rays whose cluster cannot be resolved are counted in
+                                         linear scan does (scene.glsl:134-157).  The default reports the nearest
+                                         member of such a cluster (equal t: the lower shape id) — deterministic,
+                                         but not always the one the reference's scan order picks.  Slower; rays
+                                         whose cluster cannot be resolved are counted in
                                          hjk_get_info("unresolved_ties") */
 };
 
