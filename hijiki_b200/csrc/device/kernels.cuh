@@ -78,7 +78,10 @@ struct WaveDev {
 #ifndef HJK_TRACE_MIN_BLOCKS
 #define HJK_TRACE_MIN_BLOCKS 9 /* 56 registers, no spills: 36 warps per SM (measured best of 8/9/10/12) */
 #endif
-constexpr int kTravThreads = 128;
+#ifndef HJK_TRAV_THREADS
+#define HJK_TRAV_THREADS 128
+#endif
+constexpr int kTravThreads = HJK_TRAV_THREADS;
 #ifndef HJK_SM_STACK
 #define HJK_SM_STACK 8
 #endif
