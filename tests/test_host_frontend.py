@@ -126,3 +126,37 @@ def test_synthetic_scene_shapes():
     te = hj.Scene.terrain(64).compile()
     assert te.info.num_triangles == 2 * 64 * 64 + 32 and te.info.num_emitters == 32
     assert te.array("vertices").shape[0] == 65 * 65 + 16 * 4
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "render_c")
+    lib_dir = os.path.dirname(_abi.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(_libs.ROOT, "include"),
+           os.path.join(_libs.ROOT, "examples", "render_c.c"), "-L", lib_dir, "-lhijiki_b200", f"-Wl,-rpath,{lib_dir}",
+           "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_host_compiles_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/hijiki_b200.h is plain C99 (-pedantic -Werror) and examples/render_c.c — the reference's main()
+    over the C ABI — links against the library; without a CUDA device it stops at hjk_create with a message."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is covered by the gpu-marked test")
+    r = subprocess.run([exe, _libs.CBOX_OBJ, "64", "48", "1", str(tmp_path / "o.exr")], capture_output=True, text=True)
+    assert r.returncode == 1 and "hjk_create" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_renders(tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    out = tmp_path / "o.exr"
+    r = subprocess.run([exe, _libs.CBOX_OBJ, "128", "96", "2", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Integrated 24576 paths" in r.stdout and out.stat().st_size > 128 * 96 * 12
