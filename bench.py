@@ -50,6 +50,7 @@ WORKLOADS = {
     "cbox_default": ("scenes/cbox 800x600, 64 spp, max 1000 bounces, reference defaults (BASELINE.json configs[0])", "cbox", 800, 600, 64, 1000, 64),
     "terrain": ("synthetic 10,008,370-triangle checkerboard terrain + emissive quads, 1920x1080, 64 spp, max 8 bounces (BASELINE.json configs[2])", "terrain", 1920, 1080, 64, 8, 8),
     "spheres": ("synthetic 512-sphere dielectric/mirror lattice, 3840x2160, 4096 spp, max 8 bounces (BASELINE.json configs[3])", "spheres", 3840, 2160, 4096, 8, 4),
+    "spheres64": ("synthetic 512-sphere dielectric/mirror lattice, 3840x2160, 4096 spp, max 64 bounces (SURVEY 8d: the variant that exposes path-length divergence)", "spheres", 3840, 2160, 4096, 64, 4),
 }
 # algorithmic bytes: what k_trace itself must move per ray (extension: queue entry +
 # ray in, hit record out; shadow: ray + payload in), and the whole pipeline's per-ray queue traffic
