@@ -371,7 +371,7 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
         const uint32_t hitmask = intersect_node<GUARD, false>(sc, s, q0, q1, q2, q3, q4);
         s.ng_x = __float_as_uint(q1.x);
         s.ng_y = (hitmask & 0xFF000000u) | (__float_as_uint(q0.w) >> 24);
-        s.tg_x = __float_as_uint(q1.y);
+        s.tg_x = __float_as_uint(q1.y) & kWidePrimBaseMask;
         s.tg_y = hitmask & 0x00FFFFFFu;
       } else {
         s.tg_y = 0;

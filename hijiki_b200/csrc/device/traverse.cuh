@@ -133,7 +133,10 @@ HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4&
               scz = x::as_float(((e_imask >> 16) & 0xFFu) << 23);
   const float adjx = scx * s.idx, adjy = scy * s.idy, adjz = scz * s.idz;
   float infl_x = 0.f, infl_y = 0.f, infl_z = 0.f;
-  if (GUARD) {  // sphere guard: inflation from the farthest corner of this node's frame (see trav_init)
+  // the sphere guard applies to nodes with a sphere below them; the rest of the tree holds triangles and
+  // quads only, whose tests are geometric for any direction length: plain slab test, the ray's own interval
+  const bool guarded = GUARD && (x::as_uint(q1.y) & kWideHasSpheres) != 0u;
+  if (guarded) {  // inflation from the farthest corner of this node's frame (see trav_init)
     const float fx = fmaxf(fabsf(q0.x - s.ox), fabsf(fmaf(255.0f, scx, q0.x) - s.ox));
     const float fy = fmaxf(fabsf(q0.y - s.oy), fabsf(fmaf(255.0f, scy, q0.y) - s.oy));
     const float fz = fmaxf(fabsf(q0.z - s.oz), fabsf(fmaf(255.0f, scz, q0.z) - s.oz));
@@ -149,9 +152,9 @@ HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4&
   // near planes move towards the origin, far planes away from it, by the sphere-guard inflation
   const float o0x = orgx - infl_x, o0y = orgy - infl_y, o0z = orgz - infl_z;
   const float o1x = orgx + infl_x, o1y = orgy + infl_y, o1z = orgz + infl_z;
-  const float box_tmin = GUARD ? s.box_tmin : s.tmin;
+  const float box_tmin = guarded ? s.box_tmin : s.tmin;
   const float far_t = EXACT ? fminf(s.tmax, s.t_cull) : s.tmax;
-  const float box_tmax = GUARD ? far_t * s.box_tmax_scale : far_t;
+  const float box_tmax = guarded ? far_t * s.box_tmax_scale : far_t;
   const bool nx = s.idx < 0.f, ny = s.idy < 0.f, nz = s.idz < 0.f;
   uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
@@ -391,7 +394,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       const uint32_t hitmask = intersect_node<GUARD, EXACT>(sc, s, q0, q1, q2, q3, q4);
       s.ng_x = x::as_uint(q1.x);
       s.ng_y = (hitmask & 0xFF000000u) | (x::as_uint(q0.w) >> 24);
-      s.tg_x = x::as_uint(q1.y);
+      s.tg_x = x::as_uint(q1.y) & kWidePrimBaseMask;
       s.tg_y = hitmask & 0x00FFFFFFu;
     } else {
       s.tg_x = s.ng_x, s.tg_y = s.ng_y;

@@ -306,13 +306,15 @@ struct Collapse {  // plain arrays: every entry is written by the sweep, first t
   std::unique_ptr<uint8_t[]> choice;  // 7 per node: i = 1: 0 leaf / 1 inner; i >= 2: k = roots given to
                                       // the left child, 0 = "same as i-1"
   std::unique_ptr<uint8_t[]> root8;   // per node: left share when the node becomes an inner wide node
+  std::unique_ptr<uint8_t[]> has_sphere;  // per node: a sphere among the primitives of its subtree
 };
 
-void collapse_costs(const Binary& bin, Collapse& c) {
+void collapse_costs(const Binary& bin, uint32_t n_spheres, Collapse& c) {
   const size_t n = bin.nodes.size();
   c.cost.reset(new float[n * 7]);
   c.choice.reset(new uint8_t[n * 7]);
   c.root8.reset(new uint8_t[n]);
+  c.has_sphere.reset(new uint8_t[n]);
   auto process = [&](size_t ni) {
     const Node2& nd = bin.nodes[ni];
     const float area = nd.box.half_area();
@@ -324,8 +326,10 @@ void collapse_costs(const Binary& bin, Collapse& c) {
         ch[i] = 0;
       }
       c.root8[ni] = 0;
+      c.has_sphere[ni] = bin.order[nd.first] < n_spheres;  // shape index space: spheres first
       return;
     }
+    c.has_sphere[ni] = c.has_sphere[nd.left] | c.has_sphere[nd.right];
     const float* cl = &c.cost[(size_t)nd.left * 7];
     const float* cr = &c.cost[(size_t)nd.right * 7];
     auto distribute = [&](int j, uint8_t& kbest) {  // best split of j roots between the children
@@ -582,7 +586,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
   build_binary(boxes, bin);
   lap("binary SAH build");
   Collapse col;
-  collapse_costs(bin, col);
+  collapse_costs(bin, (uint32_t)s.spheres.count, col);
   lap("collapse costs");
   out.sah_cost = col.cost[0] / std::max(bin.nodes[0].box.half_area(), 1e-30f);
 
@@ -659,7 +663,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
       scale[k] = std::ldexp(1.0, e);
     }
     wn.child_base = (uint32_t)nodes.size();
-    wn.prim_base = (uint32_t)prims.size();
+    wn.prim_base = (uint32_t)prims.size() | (col.has_sphere[cur.node2] ? kWideHasSpheres : 0u);
     uint32_t prim_off = 0, n_inner = 0;
     for (int sl = 0; sl < 8; sl++) {
       const int c = child_in_slot[sl];
@@ -836,7 +840,7 @@ bool validate_wide_bvh(const HjkScene& s, const WideBvh& bvh, std::string& err) 
           return false;
         }
         for (uint32_t i = 0; i < cnt; i++) {
-          const size_t pi = (size_t)wn.prim_base + off + i;
+          const size_t pi = (size_t)(wn.prim_base & kWidePrimBaseMask) + off + i;
           if (pi >= bvh.prims.size()) {
             err = "primitive index out of range";
             return false;
