@@ -103,7 +103,7 @@ struct HjkContext {
   float bvh_pad_rel = kDefaultBvhPadRel;
   int coop_trace = 1;    // 1 = k_trace_coop: pooled primitive tests (default mode only); 0 = per-lane k_trace
   uint32_t coop_batch_cost = 180;
-  int blocks_coop[2] = {0, 0};
+  int blocks_coop[3] = {0, 0, 0};  // k_trace_coop<GUARD = 0, 1, 2>
   int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU LBVH builder
   int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
   float bvh_build_ms = 0.f;
@@ -113,6 +113,7 @@ struct HjkContext {
   bool has_scene = false;
   SceneDev scene{};
   bool has_extinction = false;
+  bool bvh_all_guarded = false;  // every node of the wide BVH has a sphere below it (k_trace_coop<2>)
   WideBvh bvh_host_stats;  // nodes/prims cleared after upload; keeps depth etc.
   uint64_t n_nodes = 0, n_prims = 0;
   DevBuf<f4> d_nodes, d_prims, d_spheres, d_quads, d_vertices, d_emitters, d_diffuse, d_diffusecb,
@@ -386,11 +387,14 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       {
         KernelTimer t(c, stats, HJK_K_EXTEND);
         if (c->coop_trace && !exact) {
-          const int g_coop = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_coop[guard]);
-          if (guard)
-            k_trace_coop<true><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+          const int gv = guard ? (c->bvh_all_guarded ? 2 : 1) : 0;
+          const int g_coop = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_coop[gv]);
+          if (gv == 2)
+            k_trace_coop<2><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+          else if (gv == 1)
+            k_trace_coop<1><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
           else
-            k_trace_coop<false><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+            k_trace_coop<0><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
         } else if (guard && exact)
           k_trace<true, true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
         else if (guard)
@@ -616,10 +620,12 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, kTravThreads, 0);
   c->blocks_trav_v[1][1] = std::max(occ, 1);
   c->blocks_trav = c->blocks_trav_v[0][0];
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<false>, kTravThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<0>, kTravThreads, 0);
   c->blocks_coop[0] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<true>, kTravThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<1>, kTravThreads, 0);
   c->blocks_coop[1] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<2>, kTravThreads, 0);
+  c->blocks_coop[2] = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kShadeThreads, 0);
   c->blocks_tile = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
@@ -713,6 +719,7 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
     rc = build_bvh_gpu(c, info->num_spheres, info->num_quads, info->num_triangles, c->bvh_pad_rel, bvh);
     if (rc == HJK_OK) {
       built_on_gpu = true;
+      c->bvh_all_guarded = info->num_spheres != 0;  // the GPU builder flags every node of a scene with spheres
       sphere_guard_bounds(*s, bvh);
       if (c->bvh_validate && !validate_wide_bvh(*s, bvh, err))
         return c->fail(HJK_ERR_CUDA, "GPU-built BVH failed the structural check: %s", err.c_str());
@@ -726,6 +733,12 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
     if (!build_wide_bvh(*s, c->bvh_pad_rel, bvh, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
     if (bvh.depth > (uint32_t)kMaxStack)
       return c->fail(HJK_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", bvh.depth, kMaxStack);
+    c->bvh_all_guarded = !bvh.nodes.empty();
+    for (const WideNode& wn : bvh.nodes)
+      if (!(wn.prim_base & kWideHasSpheres)) {
+        c->bvh_all_guarded = false;
+        break;
+      }
     HjkArray a_nodes{bvh.nodes.data(), bvh.nodes.size()}, a_prims{bvh.prims.data(), bvh.prims.size()};
     if ((rc = upload(c, c->d_nodes, a_nodes, sizeof(WideNode)))) return rc;
     if ((rc = upload(c, c->d_prims, a_prims, sizeof(WidePrim)))) return rc;
@@ -1113,6 +1126,7 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "blocks_per_sm_tile") *out = c->blocks_tile;
   else if (k == "wave_paths") *out = (int64_t)c->wave_paths;
   else if (k == "has_extinction") *out = c->has_extinction ? 1 : 0;
+  else if (k == "sphere_guard") *out = c->scene.num_spheres ? (c->bvh_all_guarded ? 2 : 1) : 0;
   else if (k == "bvh_builder") *out = c->bvh_builder;
   else if (k == "bvh_build_us") *out = (int64_t)(c->bvh_build_ms * 1000.f);
   else if (k == "unresolved_ties") *out = (int64_t)c->unresolved_last;

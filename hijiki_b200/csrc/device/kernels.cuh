@@ -217,7 +217,7 @@ struct WaveIO {
   const f4* ray_o;  // extension rays of this bounce, in queue order
   const f4* ray_d;
   uint32_t n_shadow;
-  template <bool GUARD>
+  template <int GUARD>
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
     if (i < n_shadow) {  // dense shadow queue
       s.slot = i | kAnyHitBit;
@@ -248,7 +248,7 @@ struct BatchIO {
   const f4* ray_d;
   f4* hit;
   uint32_t flavour;  // kAnyHitBit or 0 for the whole batch
-  template <bool GUARD>
+  template <int GUARD>
   __device__ __forceinline__ void load(uint32_t i, TravState& s) const {
     s.slot = i | flavour;
     trav_init<GUARD>(s, sc, ray_o[i], ray_d[i]);
@@ -267,7 +267,7 @@ struct WarpPolicy {
 
 // Persistent warps: each warp keeps its 32 lanes supplied with rays from the work range; a lane
 // whose ray finishes is refilled as soon as fewer than `fetch_threshold` lanes are busy.
-template <bool GUARD, bool EXACT, class IO>
+template <int GUARD, bool EXACT, class IO>
 __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io, uint32_t n,
                                                uint32_t* cursor, float eps, int fetch_threshold,
                                                int postpone_lanes, uint32_t* unresolved) {
@@ -322,7 +322,7 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 // Closest hit = closer_hit (traverse.cuh): the candidate of smallest t, equal t by the lower shape id —
 // the same function of the hit set whether a primitive is tested by its own lane or by another one.
 // The exact-tie mode keeps the per-lane loop (it must record every candidate).
-template <bool GUARD, class IO>
+template <int GUARD, class IO>
 __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO& io, uint32_t n, uint32_t* cursor,
                                                     float eps, int fetch_threshold, uint32_t coop_batch_cost) {
   __shared__ uint2 sm_stack[kSmStack * kTravThreads];
@@ -491,7 +491,7 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
 // bounce in [0, max_bounces]: extension rays of `bounce` (none at max_bounces) + shadow rays of bounce-1.
 // Without the sphere guard the kernel fits 56 registers (9 CTAs = 36 warps per SM, measured best of
 // 8/9/10/12); the guard variants would spill at 56 and keep 64 registers (8 CTAs).
-template <bool GUARD, bool EXACT>
+template <int GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS)
     k_trace(WaveDev w, uint32_t bounce, uint32_t last) {
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS
                                (int)w.postpone_lanes, w.unresolved);
 }
 // same work, pooled primitive tests (traverse_queue_coop)
-template <bool GUARD>
+template <int GUARD>
 __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_COOP_MIN_BLOCKS) k_trace_coop(WaveDev w, uint32_t bounce, uint32_t last) {
   uint32_t* ctr = w.counters + (size_t)bounce * CTR_STRIDE;
   const uint32_t n_ext = bounce < last ? ctr[CTR_EXT] : 0u;
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_COOP_MIN_B
                              w.coop_batch_cost);
 }
 // cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode)
-template <bool GUARD, bool EXACT>
+template <int GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
                                                               f4* hit, uint32_t n, uint32_t* cursor, float eps,
                                                               uint32_t flavour) {

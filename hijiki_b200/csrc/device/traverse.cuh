@@ -85,8 +85,10 @@ HJK_HD float safe_rcp(float d) {
 //     s^2 >= 1:  Delta = sqrt(r_min^2 + L^2 (1 - 1/s^2)) - r_min      s^2 < 1:  Delta = r_max (1/s - 1)
 // For |s^2 - 1| of a few ulps this degenerates to a pad of ~1e-7 L^2 / r; for scenes without spheres
 // it is compiled out (triangle and quad tests are homogeneous in d, hence geometric for any s).
-// GUARD = the scene contains spheres (a per-scene constant: kernels are instantiated for both).
-template <bool GUARD>
+// GUARD (a per-scene constant the kernels are instantiated for): 0 = the scene has no spheres, 1 = some
+// subtrees hold spheres (each node says so: kWideHasSpheres), 2 = every node does (an all-sphere scene, or a
+// tree from the GPU builder): the per-node flag test is compiled out.
+template <int GUARD>
 HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const f4& d_tmax) {
   s.ox = o_tmin.x, s.oy = o_tmin.y, s.oz = o_tmin.z, s.tmin = o_tmin.w;
   s.dx = d_tmax.x, s.dy = d_tmax.y, s.dz = d_tmax.z, s.tmax = d_tmax.w;
@@ -125,7 +127,7 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
 
 // 8 child boxes of one node against the ray interval; returns the 32-bit hit mask
 // (bits 31..24: inner children in near-to-far priority order, bits 23..0: primitives).
-template <bool GUARD, bool EXACT>
+template <int GUARD, bool EXACT>
 HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4& q0, const f4& q1, const f4& q2,
                                const f4& q3, const f4& q4) {
   const uint32_t e_imask = x::as_uint(q0.w);
@@ -135,7 +137,7 @@ HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4&
   float infl_x = 0.f, infl_y = 0.f, infl_z = 0.f;
   // the sphere guard applies to nodes with a sphere below them; the rest of the tree holds triangles and
   // quads only, whose tests are geometric for any direction length: plain slab test, the ray's own interval
-  const bool guarded = GUARD && (x::as_uint(q1.y) & kWideHasSpheres) != 0u;
+  const bool guarded = GUARD == 2 || (GUARD == 1 && (x::as_uint(q1.y) & kWideHasSpheres) != 0u);
   if (guarded) {  // inflation from the farthest corner of this node's frame (see trav_init)
     const float fx = fmaxf(fabsf(q0.x - s.ox), fabsf(fmaf(255.0f, scx, q0.x) - s.ox));
     const float fy = fmaxf(fabsf(q0.y - s.oy), fabsf(fmaf(255.0f, scy, q0.y) - s.oy));
@@ -379,7 +381,7 @@ struct TravNoPolicy {
 //   Stack: push(uint32_t, uint32_t), pop(uint32_t&, uint32_t&), empty().
 // Any-hit rays (top bit of s.slot set) return at the first accepted primitive.
 // EXACT: closest-hit rays record their candidates in `cands` (TieCands) and resolve ties at the end.
-template <bool GUARD, bool EXACT, class Stack, class Policy, class Cands>
+template <int GUARD, bool EXACT, class Stack, class Policy, class Cands>
 HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, const Policy& policy, Cands& cands) {
   for (;;) {
     if (s.ng_y > 0x00FFFFFFu) {

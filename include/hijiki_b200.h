@@ -317,7 +317,7 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *                            (default 8)
  *   "blocks_per_sm_traverse", "blocks_per_sm_tile"   persistent-grid sizes
  * Info keys: "n_sms", "bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "bvh_builder", "bvh_build_us",
- *   "wave_paths", "has_extinction", "unresolved_ties", "width", "height", "device",
+ *   "wave_paths", "has_extinction", "sphere_guard" (0 no spheres, 1 per-node flag, 2 every node), "unresolved_ties", "width", "height", "device",
  *   "blocks_per_sm_traverse", "blocks_per_sm_tile". */
 HJK_API int hjk_set_option(HjkContext* ctx, const char* key, int64_t value);
 HJK_API int hjk_get_info(HjkContext* ctx, const char* key, int64_t* out_value);
