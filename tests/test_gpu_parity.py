@@ -518,3 +518,31 @@ def test_default_mode_is_order_independent(gpu_ctx, kind, max_bounces):
     assert len(set(counts)) == 1, counts
     for f in frames[1:]:
         assert np.array_equal(frames[0].view(np.uint32), f.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind,builder", [("cbox_spheres", 0), ("spheres", 0), ("cbox_spheres", 1)])
+def test_non_unit_directions_match_the_reference_arithmetic(gpu_ctx, kind, builder):
+    """Sphere guard on the device (per-node 'sphere below' flag from the host builder, every node from the GPU
+    builder): directions scaled by 1e-3 .. 1e3 — where the reference's sphere test is no longer geometric — still
+    give the reference arithmetic's first hits, off ties."""
+    compiled = _compiled(kind)
+    gpu_ctx.set_option("bvh_builder", builder)
+    try:
+        gpu_ctx.scene_upload(compiled)
+    finally:
+        gpu_ctx.set_option("bvh_builder", 0)
+    assert gpu_ctx.get_info("sphere_guard") == (2 if builder == 1 or kind == "spheres" else 1)
+    scene = _libs.HostScene.__new__(_libs.HostScene)
+    scene.view, scene.handle, scene.lib = compiled.view, None, None
+    rays = np.concatenate([_libs.camera_rays(scene, 64, 48), _random_rays(compiled, 12000, 23)])
+    rng = np.random.default_rng(5)
+    scale = np.float32(10.0) ** rng.uniform(-3, 3, rays.size).astype(np.float32)
+    scale[::7] = np.float32(1.0) + rng.uniform(-1e-6, 1e-6, scale[::7].size).astype(np.float32)
+    rays["direction"] *= scale[:, None]
+    ids_o, t_o, _, tie = _oracle_trace(compiled, rays, 2)
+    ids_g, t_g, _ = gpu_ctx.trace_first_hit(rays)
+    keep = (tie == 0) & ~np.isinf(t_o)
+    assert (ids_o[keep] == ids_g[keep]).all(), int((ids_o[keep] != ids_g[keep]).sum())
+    hit = keep & (ids_o >= 0)
+    assert (t_o[hit].view(np.uint32) == t_g[hit].view(np.uint32)).all()
+    assert (hit & (ids_o < compiled.info.num_spheres)).sum() > 100
