@@ -15,7 +15,7 @@ into it and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectSce
   e2e        the same step through the public call (`hjk_render` with a HOST block list in pinned
              memory + `hjk_readback` of the normalised frame to pinned host memory), copies in the
              timed region.
-  roofline   the dominant kernel (k_trace, BVH traversal of extension + shadow rays): algorithmic
+  roofline   the dominant kernel (k_trace_coop, BVH traversal of extension + shadow rays): algorithmic
              bytes it must move per ray / its average launch time, against the measured HBM copy peak.
   cpu_baseline / --impl reference
              the CPU restatement of the reference GLSL (oracle/, threaded-BVH2 mode = the
@@ -23,7 +23,7 @@ into it and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectSce
              The reference's own wgpu/lavapipe path cannot run in this image.
 
 Other workloads (`--workload`): cbox_default (configs[0]), terrain (configs[2], 10 M triangles),
-spheres (configs[3], 512 dielectric/mirror spheres at 3840x2160); configs[4] (reconstruction on
+spheres (configs[3], 512 dielectric/mirror spheres at 3840x2160; spheres64 = the same with max 64 bounces); configs[4] (reconstruction on
 3840x2160 feature buffers) is the `denoiser` object of every line.
 """
 from __future__ import annotations
