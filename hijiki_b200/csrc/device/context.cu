@@ -234,22 +234,66 @@ int ensure_frame(HjkContext* c, uint32_t w, uint32_t h, bool zero) {
   return HJK_OK;
 }
 
+// cuTensorMapEncodeTiled, fetched from the driver at run time (the library links the static runtime only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Tensor map of one intermediate layer for k_recon's TMA staging: the layer is [n_passes][height][width] float4,
+// described as a rank-3 fp32 tensor (4 * width floats per row, height rows, n_passes images) with a box of one
+// tile + halo; out-of-bounds elements read as zero.
+int recon_tensor_map(HjkContext* c, CUtensorMap* tm, const f4* layer, uint32_t width, uint32_t height, uint32_t n_passes,
+                     int radius) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return c->fail(HJK_ERR_CUDA, "the driver does not export cuTensorMapEncodeTiled");
+  const cuuint64_t dims[3] = {4ull * width, height, n_passes};
+  const cuuint64_t strides[2] = {16ull * width, 16ull * width * height};  // bytes, dimensions 1 and 2
+  const cuuint32_t box[3] = {4u * (uint32_t)recon_smem_pitch(radius), (uint32_t)(kReconTileY + 2 * radius), 1u};
+  const cuuint32_t elem_strides[3] = {1u, 1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<f4*>(layer), dims, strides, box, elem_strides,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return c->fail(HJK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return HJK_OK;
+}
+
 int launch_recon(HjkContext* c, const PassDev& ps, uint32_t n_passes, const f4* l0, const f4* l1, const f4* l2,
                  f4* acc) {
   if (ps.radius < 0 || ps.radius > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
-  const int pitch = kReconTileX + 2 * ps.radius, rows = kReconTileY + 2 * ps.radius;
-  const size_t smem = (size_t)pitch * rows * sizeof(f4) * (l2 ? 3 : 2);
+  const uint32_t layer_stride = recon_layer_stride(ps.radius);  // float4 elements, a multiple of 128 bytes
+  const uint32_t stages = n_passes > 1 ? 2u : 1u;
+  const size_t smem = (size_t)layer_stride * sizeof(f4) * (l2 ? 3 : 2) * stages;
+  CUtensorMap tm0, tm1, tm2;
+  int rc;
+  if ((rc = recon_tensor_map(c, &tm0, l0, ps.width, ps.height, n_passes, ps.radius))) return rc;
+  if ((rc = recon_tensor_map(c, &tm1, l1, ps.width, ps.height, n_passes, ps.radius))) return rc;
+  tm2 = tm1;
+  if (l2 && (rc = recon_tensor_map(c, &tm2, l2, ps.width, ps.height, n_passes, ps.radius))) return rc;
   dim3 block(kReconTileX, kReconTileY);
   dim3 grid((ps.width + kReconTileX - 1) / kReconTileX, (ps.height + kReconTileY - 1) / kReconTileY);
+#define HJK_RECON(A, RT)                                                                                          \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<A, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    k_recon<A, RT><<<grid, block, smem, c->stream>>>(ps, n_passes, tm0, tm1, tm2, acc);                           \
+  } while (0)
   if (l2) {
-    if (smem > 48 * 1024)
-      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_recon<true><<<grid, block, smem, c->stream>>>(ps, n_passes, l0, l1, l2, acc);
+    if (ps.radius == 2) HJK_RECON(true, 2); else HJK_RECON(true, -1);
   } else {
-    if (smem > 48 * 1024)
-      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_recon<false><<<grid, block, smem, c->stream>>>(ps, n_passes, l0, l1, nullptr, acc);
+    if (ps.radius == 2) HJK_RECON(false, 2); else HJK_RECON(false, -1);
   }
+#undef HJK_RECON
   HJK_CUDA(c, cudaGetLastError());
   return HJK_OK;
 }

@@ -207,23 +207,40 @@ HJK_HD float exp_det(float a) {
   return y;
 }
 
-// exp_det(-e) for e >= 0 (or NaN), bit for bit, with the work the sign makes unnecessary removed:
-// no overflow test, and n = round(-e log2 e) lies in [-126, 0], so 2^n is built in one piece
-// (y * 2^(n/2) * 2^(n - n/2) and y * 2^n round identically: the first product is exact).
-HJK_HD float exp_det_neg(float e) {
-  if (!(e <= 87.3365402f)) return e != e ? -e : 0.0f;
+// Bilateral weight of the reconstruction pass, exp(-e) for e >= 0 (reconstruction.glsl:54), the one
+// transcendental evaluated per filter tap (~10^8 times per 4K pass).  GLSL leaves both the precision of
+// exp() and the contraction of a*b+c to the implementation, so this one is specified on FUSED multiply-adds
+// (exactly defined in IEEE 754-2008; __fmaf_rn on the device, fmaf() in the oracle): 13 operations
+// instead of the ~30 separately rounded ones of exp_det, and < 1 ulp from the true value over the whole range
+// (tests/test_math_spec.py: 0.91 ulp).
+//   e NaN -> NaN (any payload); e > 87.3365402 -> 0; otherwise a = -e,
+//   t = fma(a, log2 e, 1.5*2^23); n = t - 1.5*2^23   (n = a*log2(e) rounded to the nearest integer, ties to even)
+//   r = fma(n, -LN2_LO, fma(n, -LN2_HI, a))          (LN2_HI = 0x1.62e4p-1 has 16 significant bits: n*LN2_HI exact)
+//   y = fma(fma(q(r), r, 1), r, 1), q = Horner(B4..B0) in fma;   result = y * 2^n (2^n built from the bits of t)
+// exp_fma_neg(0) == 1 exactly.
+HJK_HD float fma_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return ::fmaf(a, b, c);
+#endif
+}
+HJK_HD float exp_fma_neg(float e) {
+  // straight-line: a NaN e flows through every operation below, an e past the cutoff is replaced at the end
   const float a = -e;
-  float n = x::floor(x::add(x::mul(a, 1.44269504088896341f), 0.5f));
-  float r = x::sub(a, x::mul(n, 0.693359375f));
-  r = x::sub(r, x::mul(n, -2.12194440e-4f));
-  float z = x::mul(r, r);
-  float p = x::add(x::mul(1.9875691500e-4f, r), 1.3981999507e-3f);
-  p = x::add(x::mul(p, r), 8.3334519073e-3f);
-  p = x::add(x::mul(p, r), 4.1665795894e-2f);
-  p = x::add(x::mul(p, r), 1.6666665459e-1f);
-  p = x::add(x::mul(p, r), 5.0000001201e-1f);
-  float y = x::add(x::add(x::mul(p, z), r), 1.0f);
-  return x::mul(y, x::as_float((uint32_t)((int)n + 127) << 23));
+  const float t = fma_rn(a, 1.44269504088896341f, 12582912.0f);
+  const float n = x::sub(t, 12582912.0f);
+  float r = fma_rn(n, -0.693145751953125f, a);
+  r = fma_rn(n, -1.42860682030941723212e-6f, r);
+  float p = 1.384070492e-03f;
+  p = fma_rn(p, r, 8.368702605e-03f);
+  p = fma_rn(p, r, 4.166791961e-02f);
+  p = fma_rn(p, r, 1.666652113e-01f);
+  p = fma_rn(p, r, 4.999999404e-01f);
+  p = fma_rn(p, r, 1.0f);
+  const float y = fma_rn(p, r, 1.0f);
+  const float v = x::mul(y, x::as_float((x::as_uint(t) << 23) + 0x3F800000u));
+  return e > 87.3365402f ? 0.0f : v;
 }
 
 // atan on the whole line (Cephes atanf), then atan2 by quadrant.

@@ -19,6 +19,7 @@
 // No host synchronisation inside a wave: every kernel reads its element count from device
 // counters written by the previous stage.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the driver entry point is fetched at run time)
 #include <cuda_runtime.h>
 
 #include <type_traits>
@@ -712,50 +713,102 @@ struct SmemLayers {  // tile + halo staged in shared memory
 // what paid was occupancy — 32 x 8 tiles at 40 registers, 6 CTAs = 48 warps per SM (990 -> 1244 GB/s at 4K;
 // measured 16-row tiles x 2/3/4 CTAs and 8-row tiles x 4/5/6/7/8 CTAs); keeping two taps in flight per
 // thread changed nothing.
+// 16-byte shared-memory load by 32-bit shared-space address (no generic-address arithmetic per tap).  volatile:
+// keeps its place after the mbarrier wait that publishes the tile.
+__device__ __forceinline__ f4 lds16(uint32_t addr) {
+  f4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// One tap of an interior texel.  a0 = shared address of the centre texel in layer 0, layer_bytes = distance to
+// the same texel in the next layer; the tap's byte offset comes precomputed in the top half of tw.y.
 template <bool HAS_ALBEDO>
-__device__ __forceinline__ f4 recon_tap_weighted(uint2 tw, const f4* s0, const f4* s1, const f4* s2, int cidx, vec3 nc,
-                                                 vec3 ac) {
-  const int idx = cidx + ((int)tw.y >> 16);
+__device__ __forceinline__ f4 recon_tap_weighted(uint2 tw, uint32_t a0, uint32_t layer_bytes, vec3 nc, vec3 ac) {
+  const uint32_t a = a0 + (uint32_t)((int)tw.y >> 16);
   float w = __uint_as_float(tw.x);
-  const f4 cw = s0[idx];
-  const vec3 no = xyz(s1[idx]) - nc;
+  const f4 cw = lds16(a);
+  const vec3 no = xyz(lds16(a + layer_bytes)) - nc;
   float e = x::mul(dot(no, no), 2.0f);
   if (HAS_ALBEDO) {
-    const vec3 ao = xyz(s2[idx]) - ac;
+    const vec3 ao = xyz(lds16(a + 2u * layer_bytes)) - ac;
     e = x::add(e, dot(ao, ao));
   }
-  if (e != 0.f) w = x::mul(w, exp_det_neg(e));  // exp_det(-0) == 1 exactly, so the branch only saves work
+  w = x::mul(w, exp_fma_neg(e));  // exp(-e) in the FMA specification (hjk_math.cuh); exp_fma_neg(0) == 1
   return F4(x::mul(w, cw.x), x::mul(w, cw.y), x::mul(w, cw.z), x::mul(w, cw.w));
 }
 __device__ __forceinline__ f4 recon_accumulate(f4 acc, f4 wv) {  // reconstruction.glsl:55-58: NaN samples are dropped
-  if (x::is_nan(wv.x) || x::is_nan(wv.y) || x::is_nan(wv.z) || x::is_nan(wv.w)) return acc;
+  // two unordered compares cover the four components (FSETP.NAN takes two operands)
+  uint32_t bad;
+  asm("{\n\t.reg .pred p;\n\tsetp.nan.f32 p, %1, %2;\n\tsetp.nan.or.f32 p, %3, %4, p;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(bad)
+      : "f"(wv.x), "f"(wv.y), "f"(wv.z), "f"(wv.w));
+  if (bad) return acc;
   return F4(x::add(acc.x, wv.x), x::add(acc.y, wv.y), x::add(acc.z, wv.z), x::add(acc.w, wv.w));
 }
 template <bool HAS_ALBEDO>
-__device__ __forceinline__ f4 reconstruct_interior(const uint32_t* tl, const f4* s0, const f4* s1, const f4* s2,
-                                                   int cidx, f4 acc) {
-  const vec3 nc = xyz(s1[cidx]);
-  const vec3 ac = HAS_ALBEDO ? xyz(s2[cidx]) : V3(0.f);
+__device__ __forceinline__ f4 reconstruct_interior(const uint32_t* tl, uint32_t a0, uint32_t layer_bytes, f4 acc) {
+  const vec3 nc = xyz(lds16(a0 + layer_bytes));
+  const vec3 ac = HAS_ALBEDO ? xyz(lds16(a0 + 2u * layer_bytes)) : V3(0.f);
   const uint32_t n = tl[0];
   const uint2* tp = reinterpret_cast<const uint2*>(tl + 2);
+#pragma unroll 4
   for (uint32_t k = 0; k < n; k++)
-    acc = recon_accumulate(acc, recon_tap_weighted<HAS_ALBEDO>(__ldg(tp + k), s0, s1, s2, cidx, nc, ac));
+    acc = recon_accumulate(acc, recon_tap_weighted<HAS_ALBEDO>(__ldg(tp + k), a0, layer_bytes, nc, ac));
   return acc;
 }
 
-// One launch reconstructs `n_passes` consecutive passes (layers [pass][pixel]): the
-// accumulator texel stays in a register across passes, each pass' tile is staged once.
-// pass_tile_block advances by tiles_x*tiles_y per pass.  albedo may be null.
-template <bool HAS_ALBEDO>
+// ---- TMA plumbing (cp.async.bulk.tensor + mbarrier), sm_90+ PTX written out by hand
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {  // make the initialised barriers visible to the async proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// box of the rank-3 tensor (floats of a row, rows, passes) at coordinates (c0, c1, c2) -> shared memory; texels
+// outside the image arrive as zeros (the tensor map's out-of-bounds fill), negative coordinates included
+__device__ __forceinline__ void tma_load_box3(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_addr(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+      : "memory");
+}
+
+// One launch reconstructs `n_passes` consecutive passes (layers [pass][pixel]): the accumulator texel stays
+// in a register across passes.  Each pass' tile + halo of the two (three) layers is brought into shared
+// memory by the TMA engine — one elected thread issues one box copy per layer, rows outside the image are
+// zero-filled by the copy itself — double-buffered across the fused passes behind two mbarriers: pass p + 1
+// lands while pass p is filtered.  pass_tile_block advances by tiles_x*tiles_y per pass.
+// layer_stride = f4 elements between the layers of a stage (the box rounded up to 128 bytes).
+// RT = the filter radius when it is a compile-time constant (2, the reference's: src/main.rs:1284), else -1.
+HJK_HD uint32_t recon_layer_stride(int radius) {  // a layer's box in float4 elements, rounded up to 128 bytes
+  return ((uint32_t)(recon_smem_pitch(radius) * (kReconTileY + 2 * radius)) + 7u) & ~7u;
+}
+template <bool HAS_ALBEDO, int RT>
 __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS)
-    k_recon(PassDev ps, uint32_t n_passes, const f4* __restrict__ layer0, const f4* __restrict__ layer1,
-            const f4* __restrict__ layer2, f4* __restrict__ accumulator) {
-  extern __shared__ f4 smem[];
-  const int R = ps.radius;
+    k_recon(PassDev ps, uint32_t n_passes, const __grid_constant__ CUtensorMap tm0,
+            const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+            f4* __restrict__ accumulator) {
+  extern __shared__ __align__(128) f4 smem[];
+  __shared__ uint64_t full[2];
+  constexpr uint32_t NL = HAS_ALBEDO ? 3u : 2u;
+  const int R = RT >= 0 ? RT : ps.radius;
   const int pitch = recon_smem_pitch(R), rows = kReconTileY + 2 * R;
-  f4* s0 = smem;
-  f4* s1 = s0 + pitch * rows;
-  f4* s2 = s1 + pitch * rows;
+  const uint32_t layer_stride = recon_layer_stride(R);
   const int x0 = (int)blockIdx.x * kReconTileX - R, y0 = (int)blockIdx.y * kReconTileY - R;
   // a warp covers 4 x 8 texels, not 32 x 1: texels within R of a block edge run a second (or
   // fourth) block's tap list, and narrow warps keep those few texels from stalling 28 others
@@ -764,28 +817,32 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS
   const uint32_t gx = blockIdx.x * kReconTileX + 4u * (warp & 7) + (lane & 3);
   const uint32_t gy = blockIdx.y * kReconTileY + 8u * (warp >> 3) + (lane >> 2);
   const bool in_image = gx < ps.width && gy < ps.height;
-  const size_t n_pixels = (size_t)ps.width * ps.height;
+  const uint32_t tx_bytes = (uint32_t)(pitch * rows) * 16u * NL;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  auto issue = [&](uint32_t p) {  // thread 0: stage p & 1 <- tile + halo of pass p
+    f4* dst = smem + (size_t)(p & 1u) * NL * layer_stride;
+    uint64_t* bar = &full[p & 1u];
+    mbar_expect_tx(bar, tx_bytes);
+    tma_load_box3(dst, &tm0, bar, 4 * x0, y0, (int)p);
+    tma_load_box3(dst + layer_stride, &tm1, bar, 4 * x0, y0, (int)p);
+    if (HAS_ALBEDO) tma_load_box3(dst + 2 * layer_stride, &tm2, bar, 4 * x0, y0, (int)p);
+  };
+  if (tid == 0) issue(0);
   f4 acc = F4(0.f, 0.f, 0.f, 0.f);
   if (in_image) acc = accumulator[(size_t)gy * ps.width + gx];
+  const int cidx = ((int)gy - y0) * pitch + ((int)gx - x0);
   for (uint32_t p = 0; p < n_passes; p++) {
-    const f4* l0 = layer0 + p * n_pixels;
-    const f4* l1 = layer1 + p * n_pixels;
-    const f4* l2 = HAS_ALBEDO ? layer2 + p * n_pixels : nullptr;
-    for (int i = tid; i < pitch * rows; i += kReconTileX * kReconTileY) {
-      const int sy = i / pitch, sx = i - sy * pitch;
-      const int px = x0 + sx, py = y0 + sy;
-      f4 a = F4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
-      if (px >= 0 && py >= 0 && px < (int)ps.width && py < (int)ps.height) {
-        const size_t o = (size_t)py * ps.width + px;
-        a = l0[o];
-        b = l1[o];
-        if (HAS_ALBEDO) c = l2[o];
-      }
-      s0[i] = a;
-      s1[i] = b;
-      if (HAS_ALBEDO) s2[i] = c;
-    }
-    __syncthreads();
+    // stage (p + 1) & 1 was last read in iteration p - 1, which ended with a CTA barrier
+    if (tid == 0 && p + 1 < n_passes) issue(p + 1);
+    mbar_wait(&full[p & 1u], (p >> 1) & 1u);
+    const f4* s0 = smem + (size_t)(p & 1u) * NL * layer_stride;
+    const f4* s1 = s0 + layer_stride;
+    const f4* s2 = s1 + layer_stride;
     if (in_image) {
       const int32_t b = ps.tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
       bool interior = false;
@@ -796,8 +853,8 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS
                    ly + (uint32_t)R < blk.dimension[1];
       }
       if (interior) {
-        const int cidx = ((int)gy - y0) * pitch + ((int)gx - x0);
-        acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R), s0, s1, s2, cidx, acc);
+        acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R),
+                                               smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, acc);
       } else {
         const SmemLayers L{s0, s1, s2, x0, y0, pitch};
         acc = reconstruct_pixel<HAS_ALBEDO>(ps, L, gx, gy, acc);

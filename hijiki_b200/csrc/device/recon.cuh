@@ -24,7 +24,8 @@ struct PassDev {
   const uint32_t* taps;        // per block: {count, 0}, then (2R+1)^2 x {weight bits, packed offset} of the
                                // taps with weight >= 0 in loop order (recon_tap_stride words per block,
                                // 8-byte aligned pairs); packed offset = (dx+128) | (dy+128) << 8 |
-                               // int16(dy * kReconSmemPitch(R) + dx) << 16 (k_recon's shared-memory tile)
+                               // int16(16 * (dy * recon_smem_pitch(R) + dx)) << 16: the tap's BYTE offset in
+                               // k_recon's shared-memory tile of float4 texels (|.| <= 16 * 392)
   int32_t radius;
 };
 // pitch of k_recon's shared-memory tile (32 texels + halo); baked into the tap table
@@ -53,7 +54,7 @@ HJK_HD void recon_fill_block_tables(const HjkImageBlock& blk, int radius, float 
       if (w < 0.f) continue;
       taps[2 + 2 * n] = x::as_uint(w);
       taps[3 + 2 * n] = (uint32_t)(dx + 128) | ((uint32_t)(dy + 128) << 8) |
-                        ((uint32_t)(uint16_t)(int16_t)(dy * recon_smem_pitch(radius) + dx) << 16);
+                        ((uint32_t)(uint16_t)(int16_t)(16 * (dy * recon_smem_pitch(radius) + dx)) << 16);
       n++;
     }
   taps[0] = n;
@@ -70,9 +71,9 @@ HJK_HD void recon_tap(const Layers& L, uint32_t px, uint32_t py, float w, vec3 n
     const vec3 ao = xyz(L.albedo(px, py)) - ac;
     e = x::add(e, dot(ao, ao));
   }
-  if (e != 0.f) w = x::mul(w, exp_det_neg(e));  // exp_det(-0) == 1 exactly, so the branch only saves work
+  w = x::mul(w, exp_fma_neg(e));  // exp(-e) in the FMA specification (hjk_math.cuh); exp_fma_neg(0) == 1
   const f4 wv = F4(x::mul(w, cw.x), x::mul(w, cw.y), x::mul(w, cw.z), x::mul(w, cw.w));
-  if (x::is_nan(wv.x) || x::is_nan(wv.y) || x::is_nan(wv.z) || x::is_nan(wv.w)) return;
+  if (x::is_nan(wv.x) || x::is_nan(wv.y) || x::is_nan(wv.z) || x::is_nan(wv.w)) return;  // :55-58
   acc = F4(x::add(acc.x, wv.x), x::add(acc.y, wv.y), x::add(acc.z, wv.z), x::add(acc.w, wv.w));
 }
 

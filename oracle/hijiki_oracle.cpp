@@ -777,7 +777,7 @@ void reconstructBlock(const OrcBlock& blk, const OrcParams& p, SampleFn sample, 
             sample(2, sx, sy, al);
             vec3 nO = V(nd[0] - nc[0], nd[1] - nc[1], nd[2] - nc[2]);
             vec3 aO = V(al[0] - ac[0], al[1] - ac[1], al[2] - ac[2]);
-            weight *= orc_expf(-(dot(nO, nO) * 2.0f + dot(aO, aO)));  // :54
+            weight *= orc_exp_bilateral(dot(nO, nO) * 2.0f + dot(aO, aO));  // :54, exp(-(..)) in the FMA specification
             float wv[4] = {weight * cw[0], weight * cw[1], weight * cw[2], weight * cw[3]};
             if (std::isnan(wv[0]) || std::isnan(wv[1]) || std::isnan(wv[2]) || std::isnan(wv[3])) continue;
             for (int k = 0; k < 4; k++) outv[k] += wv[k];
@@ -809,6 +809,7 @@ void orc_math_eval(int fn, const float* a, const float* b, float* out, uint64_t 
       case 2: out[i] = orc_tanf(a[i]); break;
       case 3: out[i] = orc_expf(a[i]); break;
       case 4: out[i] = orc_atan2f(a[i], b[i]); break;
+      case 6: out[i] = orc_exp_bilateral(a[i]); break;
       default: out[i] = orc_asinf(a[i]); break;
     }
   }

@@ -115,7 +115,8 @@ int orc_trace_path(const OrcScene* scene, const OrcBlock* block, uint32_t lx, ui
 
 int orc_hardware_threads(void);
 
-/* orc_math.h evaluated over an array (tests).  fn: 0 sin, 1 cos, 2 tan, 3 exp, 4 atan2(a,b), 5 asin */
+/* orc_math.h evaluated over an array (tests).  fn: 0 sin, 1 cos, 2 tan, 3 exp, 4 atan2(a,b), 5 asin,
+ * 6 exp_bilateral(a) = exp(-a) in the FMA specification of the reconstruction weight */
 void orc_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n);
 
 #ifdef __cplusplus

@@ -390,6 +390,7 @@ void ht_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n
       case 2: out[i] = tan_det(a[i]); break;
       case 3: out[i] = exp_det(a[i]); break;
       case 4: out[i] = atan2_det(a[i], b[i]); break;
+      case 6: out[i] = exp_fma_neg(a[i]); break;
       default: out[i] = asin_det(a[i]); break;
     }
   }

@@ -44,16 +44,26 @@ def test_oracle_math_close_to_libm(oracle):
     assert _ulp_err(t, np.tan(tan_in.astype(np.float64))).max() <= 4.0
     a = _libs.math_eval(oracle.orc_math_eval, 5, unit)
     assert _ulp_err(a, np.arcsin(unit.astype(np.float64))).max() <= 4.0
+    # the FMA-specified exp(-e) of the reconstruction weight: faithful (< 1 ulp) on its whole range
+    pos = np.concatenate([-neg, RNG.random(400_000).astype(np.float32) * np.float32(8.0),
+                          np.float32(10.0) ** RNG.uniform(-8, 1.94, 200_000).astype(np.float32)])
+    eb = _libs.math_eval(oracle.orc_math_eval, 6, pos)
+    assert _ulp_err(eb, np.exp(-pos.astype(np.float64))).max() < 1.0
+    edge = np.array([0.0, -0.0, 87.3365402, 87.34, 88.0, 1e30, np.inf], np.float32)
+    assert np.array_equal(_libs.math_eval(oracle.orc_math_eval, 6, edge)[[0, 1, 3, 4, 5, 6]],
+                          np.array([1, 1, 0, 0, 0, 0], np.float32))
+    assert _libs.math_eval(oracle.orc_math_eval, 6, edge)[2] > 0
+    assert np.isnan(_libs.math_eval(oracle.orc_math_eval, 6, np.array([np.nan], np.float32))[0])
     at = _libs.math_eval(oracle.orc_math_eval, 4, y, x)
     assert _ulp_err(at, np.arctan2(y.astype(np.float64), x.astype(np.float64))).max() <= 4.0
 
 
-@pytest.mark.parametrize("fn", range(6))
+@pytest.mark.parametrize("fn", range(7))
 def test_product_math_matches_oracle_bitwise(oracle, hosttest, fn):
     two_pi, neg, tan_in, unit, y, x = _inputs()
-    a = [two_pi, two_pi, tan_in, neg, y, unit][fn]
+    a = [two_pi, two_pi, tan_in, neg, y, unit, -neg][fn]
     special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-30, -1e-30, 88.0, -87.0, -87.4, 0.5,
-                        -0.5, 3.1415927, 6.2831855, 1e7], dtype=np.float32)
+                        -0.5, 3.1415927, 6.2831855, 1e7, 87.3365402, 87.34, 1e-9, 5.85645], dtype=np.float32)
     a = np.concatenate([a, special])
     b = np.concatenate([x, special[::-1]]) if fn == 4 else None
     o = _libs.math_eval(oracle.orc_math_eval, fn, a, b)
