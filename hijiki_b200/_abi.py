@@ -100,13 +100,17 @@ _SIGNATURES = {
                                       C.POINTER(HjkStats)]),
     "hjk_blocks_free": (C.c_int, [_P, C.c_uint64]),
     "hjk_readback": (C.c_int, [_P, _P, C.c_uint64, C.c_int]),
+    "hjk_readback_root": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
+    "hjk_read_features": (C.c_int, [_P, C.c_int, _P, C.c_uint64]),
     "hjk_read_intermediate": (C.c_int, [_P, C.c_int, _P]),
     "hjk_trace_first_hit": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P, _P]),
+    "hjk_trace_first_hit_eps": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_float, _P, _P, _P]),
     "hjk_denoise_pass": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint64, C.POINTER(HjkParams)]),
     "hjk_denoise_upload": (C.c_int, [_P, _P, _P, _P, C.c_uint64]),
     "hjk_denoise_resident": (C.c_int, [_P, C.POINTER(HjkParams), C.c_uint32, C.POINTER(C.c_float)]),
     "hjk_comm_unique_id": (C.c_int, [_P]),
     "hjk_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "hjk_reduce_frame": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "hjk_allreduce_accumulator": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "hjk_accumulator_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hjk_synchronize": (C.c_int, [_P]),

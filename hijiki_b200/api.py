@@ -176,11 +176,13 @@ def make_params(max_bounces: int = 1000, rr_start: int = 3, recon_radius: int = 
 class Context:
     """Owner of one GPU's device state (``GPU::new``, src/main.rs:692-712)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """``device``: one CUDA device id, or a sequence of ids for a single-process multi-GPU group."""
         self.lib = _abi.load()
         self.ptr = C.c_void_p()
-        dev = (C.c_int * 1)(device)
-        rc = self.lib.hjk_create(dev, 1, C.byref(self.ptr))
+        ids = [int(device)] if isinstance(device, (int, np.integer)) else [int(d) for d in device]
+        dev = (C.c_int * len(ids))(*ids)
+        rc = self.lib.hjk_create(dev, len(ids), C.byref(self.ptr))
         if rc != 0:
             raise HijikiError(rc, self.lib.hjk_last_error(None).decode())
         self._keep = []
@@ -253,6 +255,35 @@ class Context:
     def readback_ptr(self, ptr: int, pitch: int, normalise: bool = True) -> None:
         self._check(self.lib.hjk_readback(self.ptr, C.c_void_p(ptr), pitch, int(normalise)))
 
+    def readback_root(self, root: int, normalise: bool = True, out: np.ndarray | None = None):
+        """Frame summed over the ranks and delivered to ``root`` only; the other ranks get ``None``."""
+        if self.get_info("n_ranks") > 1 and self.get_info("n_devices") == 1 and 0 <= root != self.get_info("rank"):
+            self._check(self.lib.hjk_readback_root(self.ptr, root, None, 0, int(normalise)))
+            return None
+        w, h = self.frame_size()
+        if out is None:
+            out = np.empty((h, w, 4), dtype=np.float32)
+        self._check(self.lib.hjk_readback_root(self.ptr, root, as_ptr(out), out.strides[0], int(normalise)))
+        return out
+
+    def readback_root_ptr(self, root: int, ptr: int, pitch: int, normalise: bool = True) -> None:
+        self._check(self.lib.hjk_readback_root(self.ptr, root, C.c_void_p(ptr) if ptr else None, pitch, int(normalise)))
+
+    def read_features(self, root: int = -1):
+        """Averaged first-hit (normal, depth) of the frame (option ``feature_buffers``), reduced like the frame."""
+        if self.get_info("n_ranks") > 1 and self.get_info("n_devices") == 1 and 0 <= root != self.get_info("rank"):
+            self._check(self.lib.hjk_read_features(self.ptr, root, None, 0))
+            return None
+        w, h = self.frame_size()
+        out = np.empty((h, w, 4), dtype=np.float32)
+        self._check(self.lib.hjk_read_features(self.ptr, root, as_ptr(out), out.strides[0]))
+        return out
+
+    def reduce_frame(self, root: int = -1) -> float:
+        ms = C.c_float()
+        self._check(self.lib.hjk_reduce_frame(self.ptr, root, C.byref(ms)))
+        return ms.value
+
     def read_intermediate(self, layer: int) -> np.ndarray:
         w, h = self.frame_size()
         out = np.empty((h, w, 4), dtype=np.float32)
@@ -262,16 +293,20 @@ class Context:
     def frame_size(self):
         return self.get_info("width"), self.get_info("height")
 
-    def trace_first_hit(self, rays: np.ndarray, any_hit: bool = False, exact_ties: bool = False):
+    def trace_first_hit(self, rays: np.ndarray, any_hit: bool = False, exact_ties: bool = False,
+                        eps: float | None = None):
         """Parity hook: closest hit (or occlusion) of scene.glsl:97-175 on a ray batch."""
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         n = rays.size
         ids = np.empty(n, dtype=np.int32)
         t = np.empty(n, dtype=np.float32)
         uv = np.empty((n, 2), dtype=np.float32)
-        self._check(self.lib.hjk_trace_first_hit(self.ptr, as_ptr(rays), n, int(any_hit) | (2 if exact_ties else 0),
-                                                 as_ptr(ids), as_ptr(t),
-                                                 as_ptr(uv)))
+        mode = int(any_hit) | (2 if exact_ties else 0)
+        if eps is None:
+            self._check(self.lib.hjk_trace_first_hit(self.ptr, as_ptr(rays), n, mode, as_ptr(ids), as_ptr(t), as_ptr(uv)))
+        else:
+            self._check(self.lib.hjk_trace_first_hit_eps(self.ptr, as_ptr(rays), n, mode, eps, as_ptr(ids), as_ptr(t),
+                                                         as_ptr(uv)))
         return ids, t, uv
 
     def denoise_pass(self, radiance, normal_depth, albedo, blocks, params: HjkParams) -> None:
@@ -345,13 +380,16 @@ class Renderer:
     reads back, divides by the weight and writes a 3-channel float EXR."""
 
     def __init__(self, scene: Scene, generator: ImageBlockGenerator, present_interval: int = 128,
-                 use_bvh: bool = False, device: int = 0, max_bounces: int = 1000, rank: int = 0, world: int = 1):
+                 use_bvh: bool = False, device=0, max_bounces: int = 1000, rank: int = 0, world: int = 1,
+                 comm_id: bytes | None = None):
         # present_interval drove the reference's preview window (src/main.rs:1335-1340): no-op here.
         # use_bvh selected scene.glsl's USE_BVH walk; this path always walks its own wide BVH.
         del present_interval
         self.generator = generator
         self.compiled = scene.compile(use_bvh=use_bvh)
         self.ctx = Context(device)
+        if comm_id is not None and world > 1:  # before the upload: rank 0 builds the BVH, the others receive it
+            self.ctx.comm_init(comm_id, rank, world)
         self.ctx.scene_upload(self.compiled)
         self.ctx.frame_begin(generator.width, generator.height)
         self.params = make_params(max_bounces=max_bounces)
@@ -363,6 +401,9 @@ class Renderer:
         return cls(scene, generator, present_interval, use_bvh, **kw)
 
     def render(self) -> RenderStats:
+        if len(self.blocks) == 0:  # more ranks than sample passes: this rank keeps its zeroed frame and still
+            self.stats = RenderStats(0, 0, 0, 0.0, {}, 0)  # joins the frame's collective in image()
+            return self.stats
         self.stats = self.ctx.render(self.blocks, self.params)
         return self.stats
 

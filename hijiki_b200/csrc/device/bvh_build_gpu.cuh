@@ -272,6 +272,15 @@ __device__ __forceinline__ void write_prim(const BuildScene& s, uint32_t shape, 
   *out = p;
 }
 
+// Between two levels of k_collapse: the tasks just emitted become the next level's input; counts the levels
+// that had work (no host round trip per level).  lvl[0] = n_in, lvl[1] = n_out, lvl[2] = depth.
+__global__ void k_next_level(uint32_t* lvl) {
+  const uint32_t n = lvl[1];
+  lvl[0] = n;
+  lvl[1] = 0;
+  if (n) lvl[2] += 1;
+}
+
 // counters: [0] wide nodes allocated, [1] primitive records allocated, [2] overflow flag
 // One thread per wide node of the current level.
 __global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const uint32_t* n_in, uint2* tasks_out,

@@ -10,6 +10,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../host/pass_plan.h"
@@ -31,7 +32,12 @@ struct NcclApi {
   void* handle = nullptr;
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -50,10 +56,16 @@ bool load_nccl(std::string& err) {
   }
   g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(h, "ncclCommInitAll");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.Reduce = (decltype(g_nccl.Reduce))dlsym(h, "ncclReduce");
+  g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(h, "ncclBroadcast");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommInitAll || !g_nccl.AllReduce || !g_nccl.Reduce ||
+      !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.CommDestroy) {
     err = "libnccl is missing expected symbols";
     return false;
   }
@@ -106,6 +118,7 @@ struct HjkContext {
   int blocks_coop[3] = {0, 0, 0};  // k_trace_coop<GUARD = 0, 1, 2>
   int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU LBVH builder
   int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
+  int bvh_broadcast = 1;  // several ranks: rank 0 builds the wide BVH, the others receive it over ncclBroadcast
   float bvh_build_ms = 0.f;
   uint32_t fetch_threshold = kFetchThreshold, postpone_lanes = kPostponeLanes;
 
@@ -122,7 +135,21 @@ struct HjkContext {
 
   // frame
   uint32_t width = 0, height = 0;
-  DevBuf<f4> d_acc, d_norm;
+  // [accumulator: 4 floats per texel | feature sums (normal, depth): 4 per texel | sample counts: 1 per texel]
+  DevBuf<float> d_frame;
+  DevBuf<float> d_sum;   // the same, summed over the ranks / devices of a multi-GPU frame (never aliases d_frame)
+  DevBuf<f4> d_norm;     // staging of a readback
+  bool feature_buffers = false;  // option "feature_buffers": k_recon also sums the first-hit features
+  bool reduced_valid = false;    // d_sum holds the reduction of the frame as it stands
+  int reduced_root = -2;         // ... delivered to this rank (-1 = to every rank)
+  f4* acc() const { return (f4*)d_frame.p; }
+  f4* feat() const { return (f4*)(d_frame.p + 4 * (size_t)width * height); }
+  float* cnt() const { return d_frame.p + 8 * (size_t)width * height; }
+  size_t frame_floats() const { return (size_t)width * height * (feature_buffers ? 9 : 4); }
+  // single-process multi-GPU (hjk_create with n_devices > 1): members[0] is this context, the others own one
+  // further device each; every member holds its communicator of ncclCommInitAll in `comm`
+  std::vector<HjkContext*> members;
+  HjkContext* group_parent = nullptr;
 
   // wave buffers
   DevBuf<f4> d_ray_o[2], d_ray_d[2], d_thr[2], d_ext[2], d_hit, d_layer0, d_layer1, d_sh_o, d_sh_d, d_sh_c;
@@ -130,6 +157,7 @@ struct HjkContext {
   DevBuf<unsigned long long> d_totals;  // paths, extension rays, shadow rays of the current call
   DevBuf<uint32_t> d_unresolved;        // exact-tie mode: rays whose cluster outgrew the window/list
   uint64_t unresolved_last = 0;         // ... of the last render / trace call
+  uint64_t stack_overflows = 0;         // traversal-stack entries dropped since the scene upload (must stay 0)
   DevBuf<int32_t> d_tile_block;
   DevBuf<HjkImageBlock> d_blocks;
   DevBuf<float> d_weights;
@@ -137,6 +165,11 @@ struct HjkContext {
   std::vector<uint32_t> h_counters;
   uint32_t last_wave_passes = 0;  // for hjk_read_intermediate
   bool have_features = false;
+
+  // hjk_trace_first_hit batches (grow-only)
+  DevBuf<f4> d_batch_o, d_batch_d, d_batch_h;
+  DevBuf<uint32_t> d_batch_cur;
+  std::vector<f4> h_batch_o, h_batch_d;
 
   // resident block lists
   struct Resident {
@@ -226,11 +259,12 @@ void resolve_timers(HjkContext* c, HjkStats* st) {  // after the stream has been
 
 int ensure_frame(HjkContext* c, uint32_t w, uint32_t h, bool zero) {
   const size_t n = (size_t)w * h;
-  const bool fresh = c->width != w || c->height != h || !c->d_acc.p;
-  HJK_CUDA(c, c->d_acc.ensure(n));
+  const bool fresh = c->width != w || c->height != h || !c->d_frame.p;
+  HJK_CUDA(c, c->d_frame.ensure(9 * n));
   c->width = w;
   c->height = h;
-  if (fresh || zero) HJK_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, n * sizeof(f4), c->stream));
+  if (fresh || zero) HJK_CUDA(c, cudaMemsetAsync(c->d_frame.p, 0, 9 * n * sizeof(float), c->stream));
+  c->reduced_valid = false;
   return HJK_OK;
 }
 
@@ -269,7 +303,7 @@ int recon_tensor_map(HjkContext* c, CUtensorMap* tm, const f4* layer, uint32_t w
 }
 
 int launch_recon(HjkContext* c, const PassDev& ps, uint32_t n_passes, const f4* l0, const f4* l1, const f4* l2,
-                 f4* acc) {
+                 f4* acc, bool features) {
   if (ps.radius < 0 || ps.radius > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
   const uint32_t layer_stride = recon_layer_stride(ps.radius);  // float4 elements, a multiple of 128 bytes
   const uint32_t stages = n_passes > 1 ? 2u : 1u;
@@ -282,18 +316,21 @@ int launch_recon(HjkContext* c, const PassDev& ps, uint32_t n_passes, const f4* 
   if (l2 && (rc = recon_tensor_map(c, &tm2, l2, ps.width, ps.height, n_passes, ps.radius))) return rc;
   dim3 block(kReconTileX, kReconTileY);
   dim3 grid((ps.width + kReconTileX - 1) / kReconTileX, (ps.height + kReconTileY - 1) / kReconTileY);
-#define HJK_RECON(A, RT)                                                                                          \
-  do {                                                                                                            \
-    if (smem > 48 * 1024)                                                                                         \
-      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<A, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    k_recon<A, RT><<<grid, block, smem, c->stream>>>(ps, n_passes, tm0, tm1, tm2, acc);                           \
+#define HJK_RECON(A, RT, F)                                                                                         \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      HJK_CUDA(c, cudaFuncSetAttribute(k_recon<A, RT, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_recon<A, RT, F><<<grid, block, smem, c->stream>>>(ps, n_passes, tm0, tm1, tm2, acc, c->feat(), c->cnt());     \
   } while (0)
-  if (l2) {
-    if (ps.radius == 2) HJK_RECON(true, 2); else HJK_RECON(true, -1);
+  if (l2) {  // standalone denoise with an albedo layer: no feature sums
+    if (ps.radius == 2) HJK_RECON(true, 2, false); else HJK_RECON(true, -1, false);
+  } else if (features) {
+    if (ps.radius == 2) HJK_RECON(false, 2, true); else HJK_RECON(false, -1, true);
   } else {
-    if (ps.radius == 2) HJK_RECON(false, 2); else HJK_RECON(false, -1);
+    if (ps.radius == 2) HJK_RECON(false, 2, false); else HJK_RECON(false, -1, false);
   }
 #undef HJK_RECON
+  c->reduced_valid = false;
   HJK_CUDA(c, cudaGetLastError());
   return HJK_OK;
 }
@@ -310,7 +347,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   PassPlan plan;
   std::string err;
   if (!plan_passes(blocks, n_blocks, plan, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
-  if (c->width && (c->width != plan.width || c->height != plan.height) && c->d_acc.p)
+  if (c->width && (c->width != plan.width || c->height != plan.height) && c->d_frame.p)
     return c->fail(HJK_ERR_INVALID_ARGUMENT, "blocks are for a %ux%u image but the frame is %ux%u", plan.width,
                    plan.height, c->width, c->height);
   int rc = ensure_frame(c, plan.width, plan.height, false);
@@ -355,8 +392,8 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   }
   const size_t n_ctr = ((size_t)prm->max_bounces + 1) * CTR_STRIDE;
   HJK_CUDA(c, c->d_counters.ensure(n_ctr));
-  HJK_CUDA(c, c->d_unresolved.ensure(1));
-  HJK_CUDA(c, cudaMemsetAsync(c->d_unresolved.p, 0, 4, c->stream));
+  HJK_CUDA(c, c->d_unresolved.ensure(2));  // [0] unresolved tie clusters, [1] traversal-stack overflows
+  HJK_CUDA(c, cudaMemsetAsync(c->d_unresolved.p, 0, 8, c->stream));
   HJK_CUDA(c, c->d_totals.ensure(3));
   HJK_CUDA(c, cudaMemsetAsync(c->d_totals.p, 0, 3 * sizeof(unsigned long long), c->stream));
   HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
@@ -394,7 +431,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.ext_q[0] = c->d_ext_q0.p, w.ext_q[1] = c->d_ext_q1.p;
   w.sh_o = c->d_sh_o.p, w.sh_d = c->d_sh_d.p, w.sh_c = c->d_sh_c.p;
   w.counters = c->d_counters.p;
-  w.accumulator = c->d_acc.p;
+  w.accumulator = c->acc();
   w.max_bounces = prm->max_bounces, w.rr_start = prm->rr_start;
   w.recon_radius = R;
   w.eps = prm->eps;
@@ -477,7 +514,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       ps.weights = c->d_weights.p;
       ps.taps = c->d_taps.p;
       ps.radius = R;
-      rc = launch_recon(c, ps, wp, w.layer0, w.layer1, nullptr, c->d_acc.p);
+      rc = launch_recon(c, ps, wp, w.layer0, w.layer1, nullptr, c->acc(), c->feature_buffers);
       if (rc) return rc;
       launches++;
     }
@@ -491,9 +528,10 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     if (stats) {
       unsigned long long totals[3] = {0, 0, 0};
       HJK_CUDA(c, cudaMemcpy(totals, c->d_totals.p, sizeof totals, cudaMemcpyDeviceToHost));
-      uint32_t unresolved = 0;
-      HJK_CUDA(c, cudaMemcpy(&unresolved, c->d_unresolved.p, 4, cudaMemcpyDeviceToHost));
-      c->unresolved_last = unresolved;
+      uint32_t unresolved[2] = {0, 0};
+      HJK_CUDA(c, cudaMemcpy(unresolved, c->d_unresolved.p, 8, cudaMemcpyDeviceToHost));
+      c->unresolved_last = unresolved[0];
+      c->stack_overflows += unresolved[1];
       n_paths = totals[0], n_ext = totals[1], n_sh = totals[2];
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -533,7 +571,7 @@ int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_r
   HJK_CUDA(c, vals.ensure(n));
   HJK_CUDA(c, vals_sorted.ensure(n));
   HJK_CUDA(c, pad.ensure(1));
-  const uint32_t init[16] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  const uint32_t init[16] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};  // [12] = one root task
   HJK_CUDA(c, cudaMemcpyAsync(small.p, init, sizeof init, cudaMemcpyHostToDevice, st));
   HJK_CUDA(c, cudaEventRecord(c->ev0, st));
   k_shape_boxes<<<grid, block, 0, st>>>(bs, n, blo.p, bhi.p, small.p, small.p + 6);
@@ -567,25 +605,22 @@ int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_r
   TreeDev tree{vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, ilo.p, ihi.p, icount.p};
   uint2* t_in = tasks_a.p;
   uint2* t_out = tasks_b.p;
-  uint32_t depth = 0;
-  for (;;) {
-    depth++;
-    HJK_CUDA(c, cudaMemsetAsync(small.p + 13, 0, 4, st));
+  // one launch per level, kMaxStack levels at most, no host round trip in between: a level without tasks is an
+  // empty launch; small[12] = tasks in, [13] = tasks out, [14] = levels that had work (root level included)
+  for (int level = 0; level <= kMaxStack; level++) {
     k_collapse<<<grid, block, 0, st>>>(bs, tree, t_in, small.p + 12, t_out, small.p + 13, tmp_nodes.p,
                                        (WidePrim*)c->d_prims.p, small.p + 8, node_capacity);
-    uint32_t n_next = 0;
-    HJK_CUDA(c, cudaMemcpyAsync(&n_next, small.p + 13, 4, cudaMemcpyDeviceToHost, st));
-    HJK_CUDA(c, cudaStreamSynchronize(st));
-    if (n_next == 0) break;
-    if (depth > (uint32_t)kMaxStack) return HJK_ERR_UNSUPPORTED;
-    HJK_CUDA(c, cudaMemcpyAsync(small.p + 12, small.p + 13, 4, cudaMemcpyDeviceToDevice, st));
+    k_next_level<<<1, 1, 0, st>>>(small.p + 12);
     std::swap(t_in, t_out);
   }
+  HJK_CUDA(c, cudaGetLastError());
   uint32_t fin[16];
   float pad_h = 0.f;
   HJK_CUDA(c, cudaMemcpyAsync(fin, small.p, sizeof fin, cudaMemcpyDeviceToHost, st));
   HJK_CUDA(c, cudaMemcpyAsync(&pad_h, pad.p, 4, cudaMemcpyDeviceToHost, st));
   HJK_CUDA(c, cudaStreamSynchronize(st));
+  if (fin[12] != 0) return HJK_ERR_UNSUPPORTED;  // deeper than the traversal stack: the host builder decides
+  const uint32_t depth = fin[14] + 1;
   if (fin[6]) return c->fail(HJK_ERR_INVALID_ARGUMENT, "non-finite shape bounds");
   if (fin[10] || fin[9] != n) return HJK_ERR_UNSUPPORTED;  // capacity overflow / primitive count mismatch
   const uint32_t n_nodes = fin[8];
@@ -618,24 +653,20 @@ const char* hjk_version(void) { return "hijiki_b200 0.1 (sm_100a)"; }
 
 const char* hjk_last_error(const HjkContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
-int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
-  if (!out_ctx || n_devices != 1 || !device_ids) {
-    g_create_error = "hjk_create: exactly one device per context (one process per GPU)";
-    return HJK_ERR_INVALID_ARGUMENT;
-  }
+static int create_one(int device, HjkContext** out_ctx) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
     g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
     return HJK_ERR_CUDA;
   }
-  if (device_ids[0] < 0 || device_ids[0] >= count) {
+  if (device < 0 || device >= count) {
     g_create_error = "hjk_create: device id out of range";
     return HJK_ERR_INVALID_ARGUMENT;
   }
   HjkContext* c = new (std::nothrow) HjkContext();
   if (!c) return HJK_ERR_OUT_OF_MEMORY;
-  c->device = device_ids[0];
+  c->device = device;
   auto bail = [&](const char* what, cudaError_t err) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
     delete c;
@@ -679,8 +710,7 @@ int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
   return HJK_OK;
 }
 
-int hjk_destroy(HjkContext* c) {
-  if (!c) return HJK_OK;
+static void destroy_one(HjkContext* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->resident)
@@ -691,6 +721,62 @@ int hjk_destroy(HjkContext* c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx) {
+  if (!out_ctx || n_devices < 1 || n_devices > 64 || !device_ids) {
+    g_create_error = "hjk_create: needs 1..64 device ids";
+    return HJK_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 0; i < n_devices; i++)
+    for (int j = 0; j < i; j++)
+      if (device_ids[i] == device_ids[j]) {
+        g_create_error = "hjk_create: a device is listed twice";
+        return HJK_ERR_INVALID_ARGUMENT;
+      }
+  std::vector<HjkContext*> all;
+  auto undo = [&]() {
+    for (HjkContext* m : all) destroy_one(m);
+  };
+  for (int i = 0; i < n_devices; i++) {
+    HjkContext* c = nullptr;
+    const int rc = create_one(device_ids[i], &c);
+    if (rc) {
+      undo();
+      return rc;
+    }
+    all.push_back(c);
+  }
+  if (n_devices > 1) {  // one communicator per device, created together (single process, no id exchange)
+    std::string err;
+    if (!load_nccl(err)) {
+      g_create_error = err;
+      undo();
+      return HJK_ERR_NCCL;
+    }
+    std::vector<void*> comms((size_t)n_devices, nullptr);
+    const int r = g_nccl.CommInitAll(comms.data(), n_devices, device_ids);
+    if (r != 0) {
+      g_create_error = std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+      undo();
+      return HJK_ERR_NCCL;
+    }
+    for (int i = 0; i < n_devices; i++) {
+      all[i]->comm = comms[i];
+      all[i]->rank = i, all[i]->n_ranks = n_devices;
+      all[i]->group_parent = i ? all[0] : nullptr;
+    }
+    all[0]->members = all;
+    cudaSetDevice(all[0]->device);
+  }
+  *out_ctx = all[0];
+  return HJK_OK;
+}
+
+int hjk_destroy(HjkContext* c) {
+  if (!c) return HJK_OK;
+  for (size_t i = 1; i < c->members.size(); i++) destroy_one(c->members[i]);
+  destroy_one(c);
   return HJK_OK;
 }
 
@@ -703,8 +789,11 @@ int hjk_set_stream(HjkContext* c, void* cuda_stream) {
   return HJK_OK;
 }
 
-int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
-  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+// hjk_scene_upload for one device.  shared != nullptr: upload this host-built wide BVH instead of building one
+// (the other devices of a single-process group).  keep != nullptr: hand the host-built tree back to the caller.
+// With several ranks joined and the option "bvh_broadcast" on, rank 0 alone builds; the others receive nodes and
+// primitive records over ncclBroadcast.
+static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* shared, WideBvh* keep) {
   if (!s || !s->scene.ptr || s->scene.count != 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "scene info missing");
   HJK_CUDA(c, cudaSetDevice(c->device));
   const HjkSceneInfo* info = (const HjkSceneInfo*)s->scene.ptr;
@@ -712,6 +801,11 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
       info->num_triangles != s->triangles.count || info->num_emitters != s->emitters.count)
     return c->fail(HJK_ERR_INVALID_ARGUMENT, "SceneBufferInfo counts disagree with the array counts");
   const uint64_t n_shapes = s->spheres.count + s->quads.count + s->triangles.count;
+  // sampleEmitter (scene.glsl:54-89) reads emitters[0] unconditionally at every diffuse hit: a scene without
+  // emitters has no defined result in the reference either
+  if (s->emitters.count == 0)
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "the scene has no emitter (no shape with an emissive material): "
+                                             "next-event estimation needs at least one");
   if (s->materials.count != n_shapes)
     return c->fail(HJK_ERR_INVALID_ARGUMENT, "materials must hold one word per shape");
   // validate material words and emitter table against the typed arrays they index
@@ -759,35 +853,86 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   std::string err;
   bool built_on_gpu = false;
   c->bvh_build_ms = 0.f;
-  if (c->bvh_builder == 1) {
-    rc = build_bvh_gpu(c, info->num_spheres, info->num_quads, info->num_triangles, c->bvh_pad_rel, bvh);
-    if (rc == HJK_OK) {
-      built_on_gpu = true;
-      c->bvh_all_guarded = info->num_spheres != 0;  // the GPU builder flags every node of a scene with spheres
-      sphere_guard_bounds(*s, bvh);
-      if (c->bvh_validate && !validate_wide_bvh(*s, bvh, err))
-        return c->fail(HJK_ERR_CUDA, "GPU-built BVH failed the structural check: %s", err.c_str());
-      bvh.nodes.clear();
-      bvh.prims.clear();
-    } else if (rc != HJK_ERR_UNSUPPORTED) {
-      return rc;
+  const bool bcast = c->comm && c->n_ranks > 1 && c->members.size() <= 1 && c->bvh_broadcast;
+  auto all_guarded = [](const WideBvh& b) {
+    if (b.nodes.empty()) return false;
+    for (const WideNode& wn : b.nodes)
+      if (!(wn.prim_base & kWideHasSpheres)) return false;
+    return true;
+  };
+  auto upload_tree = [&](const WideBvh& b) {
+    HjkArray a_nodes{b.nodes.data(), b.nodes.size()}, a_prims{b.prims.data(), b.prims.size()};
+    int r;
+    if ((r = upload(c, c->d_nodes, a_nodes, sizeof(WideNode)))) return r;
+    if ((r = upload(c, c->d_prims, a_prims, sizeof(WidePrim)))) return r;
+    c->n_nodes = b.nodes.size();
+    c->n_prims = b.prims.size();
+    c->bvh_all_guarded = all_guarded(b);
+    return (int)HJK_OK;
+  };
+  if (shared) {
+    if ((rc = upload_tree(*shared))) return rc;
+    bvh.depth = shared->depth, bvh.n_shapes = shared->n_shapes, bvh.pad = shared->pad, bvh.sah_cost = shared->sah_cost;
+    for (int k = 0; k < 4; k++) bvh.sph_centre[k] = shared->sph_centre[k];
+    bvh.sph_rmin = shared->sph_rmin, bvh.sph_rmax = shared->sph_rmax;
+  } else if (bcast && c->rank != 0) {
+    // nothing to build: the tree arrives below
+  } else {
+    if (c->bvh_builder == 1) {
+      rc = build_bvh_gpu(c, info->num_spheres, info->num_quads, info->num_triangles, c->bvh_pad_rel, bvh);
+      if (rc == HJK_OK) {
+        built_on_gpu = true;
+        c->bvh_all_guarded = info->num_spheres != 0;  // the GPU builder flags every node of a scene with spheres
+        sphere_guard_bounds(*s, bvh);
+        if (c->bvh_validate && !validate_wide_bvh(*s, bvh, err))
+          return c->fail(HJK_ERR_CUDA, "GPU-built BVH failed the structural check: %s", err.c_str());
+        bvh.nodes.clear();
+        bvh.prims.clear();
+      } else if (rc != HJK_ERR_UNSUPPORTED) {
+        return rc;
+      }
+    }
+    if (!built_on_gpu) {
+      if (!build_wide_bvh(*s, c->bvh_pad_rel, bvh, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+      if (bvh.depth > (uint32_t)kMaxStack)
+        return c->fail(HJK_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", bvh.depth, kMaxStack);
+      if ((rc = upload_tree(bvh))) return rc;
     }
   }
-  if (!built_on_gpu) {
-    if (!build_wide_bvh(*s, c->bvh_pad_rel, bvh, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
-    if (bvh.depth > (uint32_t)kMaxStack)
-      return c->fail(HJK_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", bvh.depth, kMaxStack);
-    c->bvh_all_guarded = !bvh.nodes.empty();
-    for (const WideNode& wn : bvh.nodes)
-      if (!(wn.prim_base & kWideHasSpheres)) {
-        c->bvh_all_guarded = false;
-        break;
-      }
-    HjkArray a_nodes{bvh.nodes.data(), bvh.nodes.size()}, a_prims{bvh.prims.data(), bvh.prims.size()};
-    if ((rc = upload(c, c->d_nodes, a_nodes, sizeof(WideNode)))) return rc;
-    if ((rc = upload(c, c->d_prims, a_prims, sizeof(WidePrim)))) return rc;
-    c->n_nodes = bvh.nodes.size();
-    c->n_prims = bvh.prims.size();
+  if (bcast) {  // header (counts, depth, sphere-guard constants), then the two arrays, root 0
+    struct Header {
+      uint32_t n_nodes, n_prims, depth, all_guarded;
+      float sph_centre[4], sph_rmin, sph_rmax, pad, sah;
+    } hd{};
+    static_assert(sizeof(Header) == 48, "header layout");
+    DevBuf<uint32_t> d_hd;
+    HJK_CUDA(c, d_hd.ensure(12));
+    if (c->rank == 0) {
+      hd.n_nodes = (uint32_t)c->n_nodes, hd.n_prims = (uint32_t)c->n_prims, hd.depth = bvh.depth;
+      hd.all_guarded = c->bvh_all_guarded ? 1u : 0u;
+      for (int k = 0; k < 4; k++) hd.sph_centre[k] = bvh.sph_centre[k];
+      hd.sph_rmin = bvh.sph_rmin, hd.sph_rmax = bvh.sph_rmax, hd.pad = bvh.pad, hd.sah = bvh.sah_cost;
+      HJK_CUDA(c, cudaMemcpyAsync(d_hd.p, &hd, sizeof hd, cudaMemcpyHostToDevice, c->stream));
+    }
+    int r = g_nccl.Broadcast(d_hd.p, d_hd.p, sizeof hd, /*ncclChar*/ 0, 0, c->comm, c->stream);
+    if (r != 0) return c->fail(HJK_ERR_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    HJK_CUDA(c, cudaMemcpyAsync(&hd, d_hd.p, sizeof hd, cudaMemcpyDeviceToHost, c->stream));
+    HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->rank != 0) {
+      HJK_CUDA(c, c->d_nodes.ensure((size_t)hd.n_nodes * 5));
+      HJK_CUDA(c, c->d_prims.ensure((size_t)hd.n_prims * HJK_PRIM_STRIDE));
+      c->n_nodes = hd.n_nodes, c->n_prims = hd.n_prims;
+      c->bvh_all_guarded = hd.all_guarded != 0;
+      bvh.depth = hd.depth, bvh.pad = hd.pad, bvh.sah_cost = hd.sah, bvh.n_shapes = (uint32_t)n_shapes;
+      for (int k = 0; k < 4; k++) bvh.sph_centre[k] = hd.sph_centre[k];
+      bvh.sph_rmin = hd.sph_rmin, bvh.sph_rmax = hd.sph_rmax;
+    }
+    r = g_nccl.GroupStart();
+    if (r == 0) r = g_nccl.Broadcast(c->d_nodes.p, c->d_nodes.p, (size_t)hd.n_nodes * sizeof(WideNode), 0, 0, c->comm, c->stream);
+    if (r == 0) r = g_nccl.Broadcast(c->d_prims.p, c->d_prims.p, (size_t)hd.n_prims * sizeof(WidePrim), 0, 0, c->comm, c->stream);
+    const int r2 = g_nccl.GroupEnd();
+    if (r != 0 || r2 != 0)
+      return c->fail(HJK_ERR_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r ? r : r2) : "error");
   }
   HJK_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
 
@@ -802,13 +947,32 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   d.camera = info->camera;
   for (int k = 0; k < 4; k++) d.sph_centre[k] = bvh.sph_centre[k];
   d.sph_rmin = bvh.sph_rmin, d.sph_rmax = bvh.sph_rmax;
+  d.postpone_limit = bvh.depth < (uint32_t)kMaxStack ? (uint32_t)kMaxStack - bvh.depth : 0u;
   c->has_extinction = has_ext;
+  if (keep) *keep = bvh;  // (empty vectors after a GPU build: the other devices of a group then build their own)
   bvh.nodes.clear();
   bvh.nodes.shrink_to_fit();
   bvh.prims.clear();
   bvh.prims.shrink_to_fit();
   c->bvh_host_stats = bvh;
+  c->stack_overflows = 0;
   c->has_scene = true;
+  return HJK_OK;
+}
+
+int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (c->members.size() <= 1) return scene_upload_impl(c, s, nullptr, nullptr);
+  // single-process group: the host builder runs once, every device gets a copy of its tree
+  WideBvh tree;
+  int rc = scene_upload_impl(c, s, nullptr, &tree);
+  if (rc) return rc;
+  for (size_t i = 1; i < c->members.size(); i++) {
+    HjkContext* m = c->members[i];
+    m->bvh_builder = c->bvh_builder, m->bvh_pad_rel = c->bvh_pad_rel, m->bvh_validate = c->bvh_validate;
+    rc = scene_upload_impl(m, s, tree.nodes.empty() ? nullptr : &tree, nullptr);
+    if (rc) return c->fail(rc, "device %d: %s", m->device, m->error.c_str());
+  }
   return HJK_OK;
 }
 
@@ -816,14 +980,84 @@ int hjk_frame_begin(HjkContext* c, uint32_t width, uint32_t height) {
   if (!c) return HJK_ERR_INVALID_ARGUMENT;
   if (width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull)
     return c->fail(HJK_ERR_INVALID_ARGUMENT, "unsupported frame size");
+  for (size_t i = 1; i < c->members.size(); i++) {
+    HjkContext* m = c->members[i];
+    m->feature_buffers = c->feature_buffers;
+    const int rc = hjk_frame_begin(m, width, height);
+    if (rc) return c->fail(rc, "device %d: %s", m->device, m->error.c_str());
+  }
   HJK_CUDA(c, cudaSetDevice(c->device));
   c->have_features = false;
   return ensure_frame(c, width, height, true);
 }
 
+// Single-process group: sample pass p of the list goes to device p mod n; one host thread per device
+// drives its wave loop, the frames meet in hjk_readback's reduction.  Devices without a pass keep their zeroed frame.
+static int render_group(HjkContext* c, const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm,
+                        HjkStats* stats) {
+  PassPlan plan;
+  std::string err;
+  if (!plan_passes(blocks, n_blocks, plan, err)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+  const size_t n = c->members.size();
+  std::vector<std::vector<HjkImageBlock>> lists(n);
+  for (size_t p = 0; p < plan.passes.size(); p++) {
+    const PassPlan::Pass& ps = plan.passes[p];
+    lists[p % n].insert(lists[p % n].end(), blocks + ps.first_block, blocks + ps.first_block + ps.n_blocks);
+  }
+  std::vector<int> rcs(n, HJK_OK);
+  std::vector<HjkStats> sts(n);
+  std::vector<std::thread> threads;
+  auto work = [&](size_t i) {
+    HjkContext* m = c->members[i];
+    memset(&sts[i], 0, sizeof(HjkStats));
+    if (lists[i].empty()) return;
+    m->profiling = c->profiling;
+    if (cudaSetDevice(m->device) != cudaSuccess) {
+      rcs[i] = m->fail(HJK_ERR_CUDA, "cudaSetDevice failed");
+      return;
+    }
+    if (m->width != plan.width || m->height != plan.height || !m->d_frame.p) {
+      rcs[i] = ensure_frame(m, plan.width, plan.height, true);
+      if (rcs[i]) return;
+    }
+    cudaError_t e = m->d_blocks.ensure(lists[i].size());
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(m->d_blocks.p, lists[i].data(), lists[i].size() * sizeof(HjkImageBlock), cudaMemcpyHostToDevice,
+                          m->stream);
+    if (e != cudaSuccess) {
+      rcs[i] = m->fail(HJK_ERR_CUDA, "block upload failed: %s", cudaGetErrorString(e));
+      return;
+    }
+    HjkParams p = *prm;
+    p.flags &= ~(uint32_t)HJK_RENDER_ASYNC;  // the block lists above live until the threads join
+    rcs[i] = render_blocks(m, lists[i].data(), m->d_blocks.p, lists[i].size(), &p, stats ? &sts[i] : nullptr);
+  };
+  for (size_t i = 1; i < n; i++) threads.emplace_back(work, i);
+  work(0);
+  for (std::thread& t : threads) t.join();
+  cudaSetDevice(c->device);
+  c->reduced_valid = false;
+  for (size_t i = 0; i < n; i++)
+    if (rcs[i]) return i ? c->fail(rcs[i], "device %d: %s", c->members[i]->device, c->members[i]->error.c_str()) : rcs[i];
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    for (size_t i = 0; i < n; i++) {
+      stats->n_paths += sts[i].n_paths;
+      stats->n_extension_rays += sts[i].n_extension_rays;
+      stats->n_shadow_rays += sts[i].n_shadow_rays;
+      stats->n_launches += sts[i].n_launches;
+      stats->ms_total = std::max(stats->ms_total, sts[i].ms_total);
+      for (int k = 0; k < HJK_N_KERNEL_SLOTS; k++) stats->kernel_ms[k] = std::max(stats->kernel_ms[k], sts[i].kernel_ms[k]);
+    }
+  }
+  return HJK_OK;
+}
+
 int hjk_render(HjkContext* c, const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm, HjkStats* stats) {
   if (!c) return HJK_ERR_INVALID_ARGUMENT;
   if (!blocks || n_blocks == 0) return c->fail(HJK_ERR_INVALID_ARGUMENT, "empty block list");
+  if (!prm) return c->fail(HJK_ERR_INVALID_ARGUMENT, "params is null");
+  if (c->members.size() > 1) return render_group(c, blocks, n_blocks, prm, stats);
   HJK_CUDA(c, cudaSetDevice(c->device));
   HJK_CUDA(c, c->d_blocks.ensure(n_blocks));
   HJK_CUDA(c, cudaMemcpyAsync(c->d_blocks.p, blocks, n_blocks * sizeof(HjkImageBlock), cudaMemcpyHostToDevice,
@@ -856,6 +1090,8 @@ int hjk_render_resident(HjkContext* c, uint64_t handle, uint64_t first_block, ui
   if (it == c->resident.end()) return c->fail(HJK_ERR_INVALID_ARGUMENT, "unknown block-list handle");
   if (n_blocks == 0 || first_block + n_blocks > it->second.host.size())
     return c->fail(HJK_ERR_INVALID_ARGUMENT, "block range out of bounds");
+  if (c->members.size() > 1)  // the resident list lives on the first device only: split it like a host list
+    return render_group(c, it->second.host.data() + first_block, n_blocks, prm, stats);
   HJK_CUDA(c, cudaSetDevice(c->device));
   return render_blocks(c, it->second.host.data() + first_block, it->second.dev + first_block, n_blocks, prm, stats);
 }
@@ -870,41 +1106,135 @@ int hjk_blocks_free(HjkContext* c, uint64_t handle) {
   return HJK_OK;
 }
 
-int hjk_allreduce_accumulator(HjkContext* c, float* out_ms) {
-  if (!c) return HJK_ERR_INVALID_ARGUMENT;
-  if (!c->d_acc.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
+// Sum of the frame (accumulator, and the feature sums + sample counts when feature_buffers is on: one
+// contiguous run of floats) over the ranks of the communicator, into d_sum — the rank's own d_frame is left as
+// it is, so a frame can be reduced and read back any number of times and rendered into afterwards.
+// root < 0: every rank receives the sum (ncclAllReduce); else only `root` does (ncclReduce).
+static int reduce_frame(HjkContext* c, int root, float* out_ms) {
   if (out_ms) *out_ms = 0.f;
+  if (!c->d_frame.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
   if (!c->comm || c->n_ranks == 1) return HJK_OK;
+  if (root >= c->n_ranks) return c->fail(HJK_ERR_INVALID_ARGUMENT, "root rank out of range");
+  if (c->reduced_valid && (c->reduced_root < 0 || c->reduced_root == root)) return HJK_OK;
   HJK_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = c->frame_floats();
+  HJK_CUDA(c, c->d_sum.ensure(9 * (size_t)c->width * c->height));
   HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  const size_t n = (size_t)c->width * c->height * 4;
-  int r = g_nccl.AllReduce(c->d_acc.p, c->d_acc.p, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream);
-  if (r != 0) return c->fail(HJK_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  int r;
+  if (root < 0)
+    r = g_nccl.AllReduce(c->d_frame.p, c->d_sum.p, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream);
+  else
+    r = g_nccl.Reduce(c->d_frame.p, c->d_sum.p, n, 7, 0, root, c->comm, c->stream);
+  if (r != 0)
+    return c->fail(HJK_ERR_NCCL, "%s: %s", root < 0 ? "ncclAllReduce" : "ncclReduce",
+                   g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
   HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-  HJK_CUDA(c, cudaEventSynchronize(c->ev1));
-  if (out_ms) cudaEventElapsedTime(out_ms, c->ev0, c->ev1);
+  if (out_ms) {
+    HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+    cudaEventElapsedTime(out_ms, c->ev0, c->ev1);
+  }
+  c->reduced_valid = true;
+  c->reduced_root = root;
   return HJK_OK;
 }
 
-int hjk_readback(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise) {
-  if (!c) return HJK_ERR_INVALID_ARGUMENT;
-  if (!c->d_acc.p) return c->fail(HJK_ERR_NO_FRAME, "hjk_readback before any frame");
-  if (!rgba || pitch_bytes < (uint64_t)c->width * 16) return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad destination");
+// The devices of a single-process group: one ncclReduce per member inside one NCCL group, all to member 0.
+static int reduce_group(HjkContext* c, float* out_ms) {
+  if (out_ms) *out_ms = 0.f;
+  if (c->reduced_valid) return HJK_OK;
+  const size_t n = c->frame_floats();
   HJK_CUDA(c, cudaSetDevice(c->device));
-  if (c->comm && c->n_ranks > 1) {
-    int rc = hjk_allreduce_accumulator(c, nullptr);
-    if (rc) return rc;
+  HJK_CUDA(c, c->d_sum.ensure(9 * (size_t)c->width * c->height));
+  HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  int r = g_nccl.GroupStart();
+  for (HjkContext* m : c->members) {
+    if (r != 0) break;
+    if (!m->d_frame.p || m->width != c->width || m->height != c->height)
+      return c->fail(HJK_ERR_NO_FRAME, "device %d has no frame of this size", m->device);
+    cudaSetDevice(m->device);
+    r = g_nccl.Reduce(m->d_frame.p, m == c ? c->d_sum.p : m->d_frame.p, n, 7, 0, 0, m->comm, m->stream);
   }
+  const int r2 = g_nccl.GroupEnd();
+  cudaSetDevice(c->device);
+  if (r != 0 || r2 != 0)
+    return c->fail(HJK_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r ? r : r2) : "error");
+  HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  if (out_ms) {
+    HJK_CUDA(c, cudaEventSynchronize(c->ev1));
+    cudaEventElapsedTime(out_ms, c->ev0, c->ev1);
+  }
+  c->reduced_valid = true;
+  c->reduced_root = 0;
+  return HJK_OK;
+}
+
+// what a readback on this context copies from: the reduced frame when there is more than one rank / device
+static const float* frame_source(const HjkContext* c) {
+  return (c->members.size() > 1 || (c->comm && c->n_ranks > 1)) ? c->d_sum.p : c->d_frame.p;
+}
+
+int hjk_reduce_frame(HjkContext* c, int root, float* out_ms) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (c->members.size() > 1) return reduce_group(c, out_ms);
+  return reduce_frame(c, root, out_ms);
+}
+
+int hjk_allreduce_accumulator(HjkContext* c, float* out_ms) { return hjk_reduce_frame(c, -1, out_ms); }
+
+static int copy_frame_out(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise) {
   const uint32_t n = c->width * c->height;
-  const f4* src = c->d_acc.p;
+  const f4* src = (const f4*)frame_source(c);
   if (normalise) {
     HJK_CUDA(c, c->d_norm.ensure(n));
-    k_normalise<<<grid_for(c, 4), 256, 0, c->stream>>>(c->d_acc.p, c->d_norm.p, n);
+    k_normalise<<<grid_for(c, 4), 256, 0, c->stream>>>(src, c->d_norm.p, n);
     HJK_CUDA(c, cudaGetLastError());
     src = c->d_norm.p;
   }
   HJK_CUDA(c, cudaMemcpy2DAsync(rgba, pitch_bytes, src, (size_t)c->width * 16, (size_t)c->width * 16, c->height,
                                 cudaMemcpyDeviceToHost, c->stream));
+  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HJK_OK;
+}
+
+int hjk_readback_root(HjkContext* c, int root, float* rgba, uint64_t pitch_bytes, int normalise) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->d_frame.p) return c->fail(HJK_ERR_NO_FRAME, "hjk_readback before any frame");
+  const bool multi_rank = c->comm && c->n_ranks > 1 && c->members.size() <= 1;
+  const bool receives = !multi_rank || root < 0 || root == c->rank;
+  if (receives && (!rgba || pitch_bytes < (uint64_t)c->width * 16))
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad destination");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  int rc = hjk_reduce_frame(c, root, nullptr);
+  if (rc) return rc;
+  if (!receives) return HJK_OK;  // the collective is enqueued; this rank's host gets nothing
+  return copy_frame_out(c, rgba, pitch_bytes, normalise);
+}
+
+int hjk_readback(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise) {
+  return hjk_readback_root(c, -1, rgba, pitch_bytes, normalise);
+}
+
+int hjk_read_features(HjkContext* c, int root, float* normal_depth, uint64_t pitch_bytes) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  if (!c->d_frame.p) return c->fail(HJK_ERR_NO_FRAME, "hjk_read_features before any frame");
+  if (!c->feature_buffers)
+    return c->fail(HJK_ERR_UNSUPPORTED, "set the option \"feature_buffers\" to 1 before the frame is rendered");
+  const bool multi_rank = c->comm && c->n_ranks > 1 && c->members.size() <= 1;
+  const bool receives = !multi_rank || root < 0 || root == c->rank;
+  if (receives && (!normal_depth || pitch_bytes < (uint64_t)c->width * 16))
+    return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad destination");
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  int rc = hjk_reduce_frame(c, root, nullptr);
+  if (rc) return rc;
+  if (!receives) return HJK_OK;
+  const uint32_t n = c->width * c->height;
+  const float* base = frame_source(c);
+  HJK_CUDA(c, c->d_norm.ensure(n));
+  k_normalise_features<<<grid_for(c, 4), 256, 0, c->stream>>>((const f4*)(base + 4 * (size_t)n), base + 8 * (size_t)n,
+                                                              c->d_norm.p, n);
+  HJK_CUDA(c, cudaGetLastError());
+  HJK_CUDA(c, cudaMemcpy2DAsync(normal_depth, pitch_bytes, c->d_norm.p, (size_t)c->width * 16, (size_t)c->width * 16,
+                                c->height, cudaMemcpyDeviceToHost, c->stream));
   HJK_CUDA(c, cudaStreamSynchronize(c->stream));
   return HJK_OK;
 }
@@ -925,29 +1255,32 @@ int hjk_read_intermediate(HjkContext* c, int layer, float* rgba) {
   return HJK_OK;
 }
 
-int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int any_hit, int32_t* shape_id,
-                        float* t, float* uv) {
+int hjk_trace_first_hit_eps(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int any_hit, float eps,
+                            int32_t* shape_id, float* t, float* uv) {
   if (!c) return HJK_ERR_INVALID_ARGUMENT;
   if (!c->has_scene) return c->fail(HJK_ERR_NO_SCENE, "hjk_trace_first_hit before hjk_scene_upload");
   if (!rays || !shape_id || n_rays == 0 || n_rays > 0x7FFFFFFFull)
     return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad ray batch");
+  if (!(eps >= 0.f)) return c->fail(HJK_ERR_INVALID_ARGUMENT, "eps must be non-negative");
   HJK_CUDA(c, cudaSetDevice(c->device));
   const size_t n = (size_t)n_rays;
-  std::vector<f4> ho(n), hd(n);
+  std::vector<f4>& ho = c->h_batch_o;
+  std::vector<f4>& hd = c->h_batch_d;
+  ho.resize(n), hd.resize(n);
   for (size_t i = 0; i < n; i++) {
     ho[i] = F4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], rays[i].t_min);
     hd[i] = F4(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2], rays[i].t_max);
   }
-  DevBuf<f4> d_o, d_d, d_h;
-  DevBuf<uint32_t> d_cur;
+  // the batch buffers belong to the context and only grow: repeated calls do not allocate
+  DevBuf<f4>&d_o = c->d_batch_o, &d_d = c->d_batch_d, &d_h = c->d_batch_h;
+  DevBuf<uint32_t>& d_cur = c->d_batch_cur;
   HJK_CUDA(c, d_o.ensure(n));
   HJK_CUDA(c, d_d.ensure(n));
   HJK_CUDA(c, d_h.ensure(n));
-  HJK_CUDA(c, d_cur.ensure(2));
+  HJK_CUDA(c, d_cur.ensure(3));  // work cursor, unresolved tie clusters, stack overflows
   HJK_CUDA(c, cudaMemcpyAsync(d_o.p, ho.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
   HJK_CUDA(c, cudaMemcpyAsync(d_d.p, hd.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
-  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 8, c->stream));
-  const float eps = 1e-4f;  // M_EPS, math.glsl:2
+  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 12, c->stream));
   const int g = grid_for(c, c->blocks_trav);
   const bool guard = c->scene.num_spheres != 0;
   const uint32_t flavour = (any_hit & 1) ? kAnyHitBit : 0u;
@@ -964,12 +1297,13 @@ int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int 
     HJK_BATCH(false, false);
 #undef HJK_BATCH
   HJK_CUDA(c, cudaGetLastError());
-  std::vector<f4> hh(n);
+  std::vector<f4>& hh = ho;  // the origins are on the device by now (same stream): reuse as the result buffer
   HJK_CUDA(c, cudaMemcpyAsync(hh.data(), d_h.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
-  uint32_t cur2[2] = {0, 0};
-  HJK_CUDA(c, cudaMemcpyAsync(cur2, d_cur.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  uint32_t cur3[3] = {0, 0, 0};
+  HJK_CUDA(c, cudaMemcpyAsync(cur3, d_cur.p, 12, cudaMemcpyDeviceToHost, c->stream));
   HJK_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->unresolved_last = cur2[1];
+  c->unresolved_last = cur3[1];
+  c->stack_overflows += cur3[2];
   for (size_t i = 0; i < n; i++) {
     int32_t id;
     memcpy(&id, &hh[i].x, 4);
@@ -985,6 +1319,11 @@ int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int 
     }
   }
   return HJK_OK;
+}
+
+int hjk_trace_first_hit(HjkContext* c, const HjkRay* rays, uint64_t n_rays, int any_hit, int32_t* shape_id,
+                        float* t, float* uv) {
+  return hjk_trace_first_hit_eps(c, rays, n_rays, any_hit, 1e-4f /* M_EPS, math.glsl:2 */, shape_id, t, uv);
 }
 
 static int denoise_apply(HjkContext* c, const HjkParams* prm, uint32_t repeat, float* out_ms) {
@@ -1018,7 +1357,7 @@ static int denoise_apply(HjkContext* c, const HjkParams* prm, uint32_t repeat, f
   ps.radius = R;
   HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   for (uint32_t i = 0; i < repeat; i++) {
-    rc = launch_recon(c, ps, 1, c->d_dn0.p, c->d_dn1.p, c->dn_has_albedo ? c->d_dn2.p : nullptr, c->d_acc.p);
+    rc = launch_recon(c, ps, 1, c->d_dn0.p, c->d_dn1.p, c->dn_has_albedo ? c->d_dn2.p : nullptr, c->acc(), false);
     if (rc) return rc;
   }
   HJK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
@@ -1088,6 +1427,7 @@ int hjk_comm_unique_id(void* out_id128) {
 int hjk_comm_init(HjkContext* c, const void* id128, int rank, int n_ranks) {
   if (!c) return HJK_ERR_INVALID_ARGUMENT;
   if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return c->fail(HJK_ERR_INVALID_ARGUMENT, "bad rank/size");
+  if (c->comm) return c->fail(HJK_ERR_INVALID_ARGUMENT, "the context already has a communicator");
   std::string err;
   if (!load_nccl(err)) return c->fail(HJK_ERR_NCCL, "%s", err.c_str());
   HJK_CUDA(c, cudaSetDevice(c->device));
@@ -1102,8 +1442,8 @@ int hjk_comm_init(HjkContext* c, const void* id128, int rank, int n_ranks) {
 
 int hjk_accumulator_device_ptr(HjkContext* c, uint64_t* out_ptr, uint64_t* out_n_floats) {
   if (!c) return HJK_ERR_INVALID_ARGUMENT;
-  if (!c->d_acc.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
-  if (out_ptr) *out_ptr = (uint64_t)(uintptr_t)c->d_acc.p;
+  if (!c->d_frame.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
+  if (out_ptr) *out_ptr = (uint64_t)(uintptr_t)c->acc();
   if (out_n_floats) *out_n_floats = (uint64_t)c->width * c->height * 4;
   return HJK_OK;
 }
@@ -1123,6 +1463,10 @@ int hjk_set_profiling(HjkContext* c, int enabled) {
 
 int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   if (!c || !key) return HJK_ERR_INVALID_ARGUMENT;
+  for (size_t i = 1; i < c->members.size(); i++) {  // a group's options apply to every device
+    const int rc = hjk_set_option(c->members[i], key, value);
+    if (rc) return c->fail(rc, "%s", c->members[i]->error.c_str());
+  }
   const std::string k(key);
   if (k == "wave_paths") {
     if (value < 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "wave_paths must be positive");
@@ -1140,6 +1484,11 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
     c->bvh_builder = (int)value;
   } else if (k == "bvh_validate") {
     c->bvh_validate = value != 0;
+  } else if (k == "bvh_broadcast") {  // several ranks: 1 = rank 0 builds and broadcasts the wide BVH (default)
+    c->bvh_broadcast = value != 0;
+  } else if (k == "feature_buffers") {  // sum the first-hit (normal, depth) per texel; takes effect at hjk_frame_begin
+    c->feature_buffers = value != 0;
+    c->reduced_valid = false;
   } else if (k == "fetch_threshold") {
     if (value < 0 || value > 32) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->fetch_threshold = (uint32_t)value;
@@ -1174,7 +1523,12 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "bvh_builder") *out = c->bvh_builder;
   else if (k == "bvh_build_us") *out = (int64_t)(c->bvh_build_ms * 1000.f);
   else if (k == "unresolved_ties") *out = (int64_t)c->unresolved_last;
+  else if (k == "stack_overflows") *out = (int64_t)c->stack_overflows;
   else if (k == "device") *out = c->device;
+  else if (k == "n_devices") *out = c->members.empty() ? 1 : (int64_t)c->members.size();
+  else if (k == "rank") *out = c->rank;
+  else if (k == "n_ranks") *out = c->n_ranks;
+  else if (k == "feature_buffers") *out = c->feature_buffers ? 1 : 0;
   else if (k == "width") *out = c->width;
   else if (k == "height") *out = c->height;
   else return c->fail(HJK_ERR_INVALID_ARGUMENT, "unknown info key '%s'", key);

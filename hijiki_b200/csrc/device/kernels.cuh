@@ -70,7 +70,8 @@ struct WaveDev {
   uint32_t fetch_threshold;      // refill a warp when fewer lanes than this are busy
   uint32_t postpone_lanes;       // postpone primitive tests that fewer lanes than this would run
   uint32_t coop_batch_cost;      // pooled primitive tests: assumed instructions per batch of 32 (0 = always pool)
-  uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
+  uint32_t* unresolved;          // [0] exact-tie mode: rays whose tie cluster outgrew the window/list;
+                                 // [1] traversal-stack entries that did not fit (must stay 0)
 };
 
 #ifndef HJK_TRACE_COOP_MIN_BLOCKS
@@ -188,11 +189,16 @@ struct DevStack {
   uint2* sm;  // this thread's column of the shared-memory stack (stride kTravThreads)
   uint2 local[kLocalStack];
   int n;
+  uint32_t* overflow;  // device counter: entries that did not fit (a lost entry can lose a hit: reported, see
+                       // hjk_get_info("stack_overflows"); hjk_scene_upload refuses trees that could get here)
+  __device__ __forceinline__ int size() const { return n; }
   __device__ __forceinline__ void push(uint32_t a, uint32_t b) {
     if (n < kSmStack) {
       sm[n * kTravThreads] = make_uint2(a, b);
     } else if (n < kMaxStack) {
       local[n - kSmStack] = make_uint2(a, b);
+    } else {
+      atomicAdd(overflow, 1u);
     }
     n++;
   }
@@ -277,6 +283,7 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
   DevStack st;
   st.sm = sm_stack + threadIdx.x;
   st.n = 0;
+  st.overflow = unresolved + 1;
   TravState s;
   typename std::conditional<EXACT, TieCands, NoCands>::type cands;
   cands.reset();
@@ -325,7 +332,8 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 // The exact-tie mode keeps the per-lane loop (it must record every candidate).
 template <int GUARD, class IO>
 __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO& io, uint32_t n, uint32_t* cursor,
-                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost) {
+                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost,
+                                                    uint32_t* unresolved) {
   __shared__ uint2 sm_stack[kSmStack * kTravThreads];
   __shared__ unsigned long long sm_best[kTravThreads];
   const uint32_t lane = threadIdx.x & 31u;
@@ -333,13 +341,14 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
   DevStack st;
   st.sm = sm_stack + threadIdx.x;
   st.n = 0;
+  st.overflow = unresolved + 1;
   TravState s;
   s.tg_y = 0, s.ng_y = 0;
   bool active = false, exhausted = false;
   for (;;) {
     // ---- refill
     const uint32_t busy = __ballot_sync(FULL, active);
-    if (!exhausted && __popc(busy) < fetch_threshold) {
+    if (!exhausted && (busy == 0u || __popc(busy) < fetch_threshold)) {  // an idle warp always refills (threshold 0)
       const uint32_t need = ~busy;
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(need));
@@ -510,9 +519,9 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_COOP_MIN_B
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
   const WaveIO io{w, w.ray_o[bounce & 1u], w.ray_d[bounce & 1u], n_shadow};
   traverse_queue_coop<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
-                             w.coop_batch_cost);
+                             w.coop_batch_cost, w.unresolved);
 }
-// cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode)
+// cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode), cursor[2] = stack overflows
 template <int GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
                                                               f4* hit, uint32_t n, uint32_t* cursor, float eps,
@@ -798,11 +807,13 @@ __device__ __forceinline__ void tma_load_box3(void* dst, const CUtensorMap* tm, 
 HJK_HD uint32_t recon_layer_stride(int radius) {  // a layer's box in float4 elements, rounded up to 128 bytes
   return ((uint32_t)(recon_smem_pitch(radius) * (kReconTileY + 2 * radius)) + 7u) & ~7u;
 }
-template <bool HAS_ALBEDO, int RT>
+// FEAT: also sum the texel's own first-hit features over the passes (feature_sum += (normal, depth),
+// sample_count += layer 0's w) — the averaged feature buffers a multi-GPU frame reduces with the accumulator.
+template <bool HAS_ALBEDO, int RT, bool FEAT>
 __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS)
     k_recon(PassDev ps, uint32_t n_passes, const __grid_constant__ CUtensorMap tm0,
             const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-            f4* __restrict__ accumulator) {
+            f4* __restrict__ accumulator, f4* __restrict__ feature_sum, float* __restrict__ sample_count) {
   extern __shared__ __align__(128) f4 smem[];
   __shared__ uint64_t full[2];
   constexpr uint32_t NL = HAS_ALBEDO ? 3u : 2u;
@@ -833,8 +844,12 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS
     if (HAS_ALBEDO) tma_load_box3(dst + 2 * layer_stride, &tm2, bar, 4 * x0, y0, (int)p);
   };
   if (tid == 0) issue(0);
-  f4 acc = F4(0.f, 0.f, 0.f, 0.f);
-  if (in_image) acc = accumulator[(size_t)gy * ps.width + gx];
+  f4 acc = F4(0.f, 0.f, 0.f, 0.f), feat = acc;
+  float cnt = 0.f;
+  if (in_image) {
+    acc = accumulator[(size_t)gy * ps.width + gx];
+    if (FEAT) feat = feature_sum[(size_t)gy * ps.width + gx], cnt = sample_count[(size_t)gy * ps.width + gx];
+  }
   const int cidx = ((int)gy - y0) * pitch + ((int)gx - x0);
   for (uint32_t p = 0; p < n_passes; p++) {
     // stage (p + 1) & 1 was last read in iteration p - 1, which ended with a CTA barrier
@@ -844,6 +859,11 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS
     const f4* s1 = s0 + layer_stride;
     const f4* s2 = s1 + layer_stride;
     if (in_image) {
+      if (FEAT) {  // a texel without a sample in this pass holds zeros in both layers (k_raygen)
+        const f4 f = s1[cidx];
+        feat = F4(x::add(feat.x, f.x), x::add(feat.y, f.y), x::add(feat.z, f.z), x::add(feat.w, f.w));
+        cnt = x::add(cnt, s0[cidx].w);
+      }
       const int32_t b = ps.tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
       bool interior = false;
       if (b >= 0) {
@@ -863,7 +883,19 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS
     __syncthreads();
     ps.tile_block += (size_t)ps.tiles_x * ps.tiles_y;
   }
-  if (in_image) accumulator[(size_t)gy * ps.width + gx] = acc;
+  if (in_image) {
+    accumulator[(size_t)gy * ps.width + gx] = acc;
+    if (FEAT) feature_sum[(size_t)gy * ps.width + gx] = feat, sample_count[(size_t)gy * ps.width + gx] = cnt;
+  }
+}
+
+// averaged features: (sum normal / n, sum depth / n); texels never sampled read as zeros
+__global__ void k_normalise_features(const f4* sum, const float* cnt, f4* out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const f4 a = sum[i];
+    const float c = cnt[i];
+    out[i] = c > 0.f ? F4(x::div(a.x, c), x::div(a.y, c), x::div(a.z, c), x::div(a.w, c)) : F4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 // save_image's divide (reference src/main.rs:1399): (r/w, g/w, b/w, w)

@@ -220,8 +220,12 @@ typedef struct HjkContext HjkContext;
 
 /* --------------------------------------------------------- context (GPU) */
 
-/* Replaces GPU::new (src/main.rs:692-712).  n_devices must be 1 per context;
- * multi-GPU runs use one context per process/GPU joined by hjk_comm_init. */
+/* Replaces GPU::new (src/main.rs:692-712).  n_devices == 1: one GPU per context; multi-GPU runs then use one
+ * context per process joined by hjk_comm_init.  n_devices > 1: a single-process GROUP over the listed devices
+ * (ncclCommInitAll): hjk_scene_upload builds the wide BVH once and copies it to every device, hjk_render sends
+ * sample pass p of the list to device p mod n_devices (one host thread per device), hjk_readback sums the
+ * frames onto the first device (one ncclReduce per frame) and copies from there.  hjk_trace_first_hit, the
+ * standalone denoise entries and hjk_read_intermediate of a group run on its first device. */
 HJK_API int hjk_create(const int* device_ids, int n_devices, HjkContext** out_ctx);
 HJK_API int hjk_destroy(HjkContext* ctx);
 
@@ -254,8 +258,19 @@ HJK_API int hjk_blocks_free(HjkContext* ctx, uint64_t handle);
 /* Replaces save_image's copy + map + divide (src/main.rs:1357-1400).
  * rgba: HOST destination, `pitch_bytes` per row (>= width*16).  normalise != 0
  * writes (r/w, g/w, b/w, w) like src/main.rs:1399, else the raw (sum w*rgb, sum w).
- * When hjk_comm_init joined several ranks this first all-reduces the accumulator. */
+ * When hjk_comm_init joined several ranks this first sums the frame over the ranks (a collective: every rank
+ * must call it).  The sum goes to a buffer of its own, the rank's frame is left untouched: reading back twice,
+ * or rendering more passes and reading back again, gives the right frame each time. */
 HJK_API int hjk_readback(HjkContext* ctx, float* rgba, uint64_t pitch_bytes, int normalise);
+/* The same with the sum delivered to rank `root` only (ncclReduce instead of ncclAllReduce): only the root's
+ * `rgba` is written, so W*H*16 bytes cross PCIe once per frame, not once per rank.  The other ranks may pass
+ * NULL.  root < 0 = hjk_readback. */
+HJK_API int hjk_readback_root(HjkContext* ctx, int root, float* rgba, uint64_t pitch_bytes, int normalise);
+/* Feature buffers of the frame (option "feature_buffers" = 1 before hjk_frame_begin): per texel the mean over
+ * its samples of layer 1 = (first-hit normal, depth) (render.glsl:173) — summed by the reconstruction kernel,
+ * reduced over ranks/devices together with the accumulator (one collective carries both), divided by the
+ * sample count here.  Same `root` rule as hjk_readback_root. */
+HJK_API int hjk_read_features(HjkContext* ctx, int root, float* normal_depth, uint64_t pitch_bytes);
 
 /* Intermediate layers of the LAST pass rendered with HJK_RENDER_KEEP_FEATURES:
  * layer 0 = (radiance, 1), layer 1 = (normal, depth), layer 2 = (albedo == 0, 0)
@@ -268,6 +283,9 @@ HJK_API int hjk_read_intermediate(HjkContext* ctx, int layer, float* rgba);
  * instead and writes 0/1 into shape_id; bit 1 selects the exact-tie mode of HJK_RENDER_EXACT_TIES. */
 HJK_API int hjk_trace_first_hit(HjkContext* ctx, const HjkRay* rays, uint64_t n_rays, int any_hit,
                                 int32_t* shape_id, float* t, float* uv);
+/* The same with M_EPS (math.glsl:2; 1e-4 above) as a parameter: the tie window of the exact mode. */
+HJK_API int hjk_trace_first_hit_eps(HjkContext* ctx, const HjkRay* rays, uint64_t n_rays, int any_hit, float eps,
+                                    int32_t* shape_id, float* t, float* uv);
 
 /* Replaces ReconstructionPipeline::run (src/main.rs:992-1003) as a standalone
  * entry: splats caller-supplied full-frame intermediate layers (HOST pointers,
@@ -287,15 +305,20 @@ HJK_API int hjk_denoise_resident(HjkContext* ctx, const HjkParams* params, uint3
 /* ------------------------------------------------------------ multi-GPU */
 
 /* One process per GPU.  Rank 0 calls hjk_comm_unique_id (128 bytes), the host
- * program broadcasts it, every rank calls hjk_comm_init.  hjk_readback then
- * performs one ncclAllReduce(sum, float) over the accumulator per frame. */
+ * program broadcasts it, every rank calls hjk_comm_init.  From then on
+ *   - hjk_scene_upload is a collective: rank 0 builds the wide BVH and the others receive nodes and primitive
+ *     records over ncclBroadcast (option "bvh_broadcast" = 0: every rank builds its own);
+ *   - hjk_readback / hjk_readback_root / hjk_read_features sum the frame over the ranks, once per frame. */
 HJK_API int hjk_comm_unique_id(void* out_id128);
 HJK_API int hjk_comm_init(HjkContext* ctx, const void* id128, int rank, int n_ranks);
-/* Explicit all-reduce of the accumulator (what hjk_readback does first). out_ms optional. */
-HJK_API int hjk_allreduce_accumulator(HjkContext* ctx, float* out_ms);
+/* The frame's reduction on its own (what the readbacks do first; a no-op when the frame has not changed since
+ * the last one).  root < 0: ncclAllReduce, else ncclReduce to `root`.  out_ms optional (device time). */
+HJK_API int hjk_reduce_frame(HjkContext* ctx, int root, float* out_ms);
+HJK_API int hjk_allreduce_accumulator(HjkContext* ctx, float* out_ms); /* = hjk_reduce_frame(ctx, -1, out_ms) */
 
-/* Device pointer / stream of the accumulator so a host framework that already
- * owns a communicator (e.g. torch.distributed) can reduce it in place. */
+/* Device pointer of this rank's accumulator so a host framework that already owns a communicator (e.g.
+ * torch.distributed) can reduce it in place (only without hjk_comm_init: with it the readbacks read the
+ * library's own sum). */
 HJK_API int hjk_accumulator_device_ptr(HjkContext* ctx, uint64_t* out_ptr, uint64_t* out_n_floats);
 HJK_API int hjk_synchronize(HjkContext* ctx);
 /* Run on a stream the host owns (a cudaStream_t, e.g. torch.cuda.Stream.cuda_stream) instead
@@ -308,8 +331,11 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *   "wave_paths"             camera paths rendered per wave (default 64 Mi = 13 GB of path state)
  *   "bvh_builder"            0 = host SAH builder (default), 1 = GPU LBVH builder; next hjk_scene_upload
  *   "bvh_validate"           1 = run the host structural check on a GPU-built tree
+ *   "bvh_broadcast"          several ranks: 1 = rank 0 builds and broadcasts the wide BVH (default), 0 = every rank builds
+ *   "feature_buffers"        1 = sum the first-hit (normal, depth) per texel for hjk_read_features (default 0)
  *   "bvh_pad_rel_e9"         outward pad of primitive boxes, in 1e-9 of the scene extent (default 10000)
- *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default 20)
+ *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default 20; an idle
+ *                            warp always refills, so 0 is valid)
  *   "coop_trace"             1 = k_trace_coop (default): a warp pools the primitive tests of its leaves and
  *                            spreads them over all 32 lanes when that is cheaper; 0 = per-lane k_trace
  *   "coop_batch_cost"        assumed instructions per pooled batch of 32 tests (default 180; 0 = always pool)
@@ -318,7 +344,9 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *   "blocks_per_sm_traverse", "blocks_per_sm_tile"   persistent-grid sizes
  * Info keys: "n_sms", "bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "bvh_builder", "bvh_build_us",
  *   "wave_paths", "has_extinction", "sphere_guard" (0 no spheres, 1 per-node flag, 2 every node), "unresolved_ties", "width", "height", "device",
- *   "blocks_per_sm_traverse", "blocks_per_sm_tile". */
+ *   "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_devices", "rank", "n_ranks", "feature_buffers",
+ *   "stack_overflows" (traversal-stack entries that did not fit since the scene upload: must read 0 — the
+ *   upload refuses trees deeper than the 32-entry stack and primitive postponing stops short of it). */
 HJK_API int hjk_set_option(HjkContext* ctx, const char* key, int64_t value);
 HJK_API int hjk_get_info(HjkContext* ctx, const char* key, int64_t* out_value);
 HJK_API const char* hjk_version(void);

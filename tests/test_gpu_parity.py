@@ -546,3 +546,77 @@ def test_non_unit_directions_match_the_reference_arithmetic(gpu_ctx, kind, build
     hit = keep & (ids_o >= 0)
     assert (t_o[hit].view(np.uint32) == t_g[hit].view(np.uint32)).all()
     assert (hit & (ids_o < compiled.info.num_spheres)).sum() > 100
+
+
+def test_scene_without_emitters_is_refused(gpu_ctx):
+    """sampleEmitter (scene.glsl:54-89) reads emitters[0] at every diffuse hit: a scene without an emissive shape
+    has no defined result in the reference; the upload refuses it instead of reading unwritten memory."""
+    D = _abi.MAT_DIFFUSE
+    verts = [(-1, 0, 0, 0, 0, 0, 1, 0), (1, 0, 0, 1, 0, 0, 1, 0), (0, 1, 0, 0, 0, 0, 1, 1)]
+    half = 0.0
+    scene = _libs.CustomScene(((0.0, 0.3, 4.0), (np.sin(half), 0.0, 0.0, np.cos(half)), 40.0), triangles=[(0, 1, 2)],
+                              vertices=verts, materials=[(D, 0)], diffuse=[(0.5, 0.5, 0.5, 0)])
+    assert scene.info.num_emitters == 0
+    with pytest.raises(hj.HijikiError) as e:
+        gpu_ctx.scene_upload(scene)
+    assert e.value.status == -1 and "emitter" in str(e.value)
+    gpu_ctx.scene_upload(_compiled("cbox"))  # the context is still usable
+
+
+@pytest.mark.parametrize("threshold", [0, 1, 32])
+def test_fetch_threshold_extremes_terminate_and_match(gpu_ctx, threshold):
+    """Option fetch_threshold over its whole accepted range (0 used to leave an idle warp without work for ever):
+    same frame as the default, bit for bit."""
+    compiled = _compiled("cbox_spheres")
+    gpu_ctx.scene_upload(compiled)
+    w, h = 136, 100
+    blocks = hj.ImageBlockGenerator(w, h, 64, 2).blocks()
+    gpu_ctx.frame_begin(w, h)
+    gpu_ctx.render(blocks, hj.make_params(max_bounces=12))
+    want = gpu_ctx.readback(normalise=False)
+    gpu_ctx.set_option("fetch_threshold", threshold)
+    try:
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.render(blocks, hj.make_params(max_bounces=12))
+        got = gpu_ctx.readback(normalise=False)
+    finally:
+        gpu_ctx.set_option("fetch_threshold", 20)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert gpu_ctx.get_info("stack_overflows") == 0
+
+
+def test_feature_buffers_average_the_first_hit_features(gpu_ctx):
+    """Option feature_buffers: hjk_read_features returns, per texel, the mean over its samples of layer 1 =
+    (normal, depth) (render.glsl:173) — checked against the oracle's per-pass layers."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h, bs, spp = 128, 96, 64, 3
+    gen = hj.ImageBlockGenerator(w, h, bs, spp)
+    blocks = gen.blocks()
+    gpu_ctx.set_option("feature_buffers", 1)
+    try:
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.render(blocks, hj.make_params(max_bounces=4))
+        feat = gpu_ctx.read_features()
+        acc = gpu_ctx.readback(normalise=False)
+    finally:
+        gpu_ctx.set_option("feature_buffers", 0)
+    O = _libs.oracle()
+    op = _libs.orc_params(max_bounces=4, use_bvh=0, block_size=bs)
+    total = np.zeros((h, w, 4), np.float32)
+    for p in range(spp):
+        one = np.ascontiguousarray(blocks[p * gen.blocks_per_pass:(p + 1) * gen.blocks_per_pass])
+        layers = np.zeros((3, h, w, 4), np.float32)
+        assert O.orc_integrate_frame(C.byref(compiled.view), _libs.ptr(one), one.size, C.byref(op), _libs.ptr(layers),
+                                     None, 0) == 0
+        total = total + layers[1]
+    want = total / np.float32(spp)
+    bad = (want.view(np.uint32) != feat.view(np.uint32)).any(axis=2).sum()
+    print(f"feature buffers: texels differing from the oracle's mean {int(bad)}/{w * h}")
+    assert bad <= 6  # a tie at the first hit can move one texel's normal
+    # the accumulator is the same frame with or without the feature sums
+    gpu_ctx.frame_begin(w, h)
+    gpu_ctx.render(blocks, hj.make_params(max_bounces=4))
+    assert np.array_equal(acc.view(np.uint32), gpu_ctx.readback(normalise=False).view(np.uint32))
+    with pytest.raises(hj.HijikiError):
+        gpu_ctx.read_features()  # option off
