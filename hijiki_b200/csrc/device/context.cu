@@ -157,7 +157,6 @@ struct HjkContext {
   DevBuf<unsigned long long> d_totals;  // paths, extension rays, shadow rays of the current call
   DevBuf<uint32_t> d_unresolved;        // exact-tie mode: rays whose cluster outgrew the window/list
   uint64_t unresolved_last = 0;         // ... of the last render / trace call
-  uint64_t stack_overflows = 0;         // traversal-stack entries dropped since the scene upload (must stay 0)
   DevBuf<int32_t> d_tile_block;
   DevBuf<HjkImageBlock> d_blocks;
   DevBuf<float> d_weights;
@@ -392,8 +391,8 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   }
   const size_t n_ctr = ((size_t)prm->max_bounces + 1) * CTR_STRIDE;
   HJK_CUDA(c, c->d_counters.ensure(n_ctr));
-  HJK_CUDA(c, c->d_unresolved.ensure(2));  // [0] unresolved tie clusters, [1] traversal-stack overflows
-  HJK_CUDA(c, cudaMemsetAsync(c->d_unresolved.p, 0, 8, c->stream));
+  HJK_CUDA(c, c->d_unresolved.ensure(1));
+  HJK_CUDA(c, cudaMemsetAsync(c->d_unresolved.p, 0, 4, c->stream));
   HJK_CUDA(c, c->d_totals.ensure(3));
   HJK_CUDA(c, cudaMemsetAsync(c->d_totals.p, 0, 3 * sizeof(unsigned long long), c->stream));
   HJK_CUDA(c, c->d_tile_block.ensure(plan.tile_block.size()));
@@ -436,7 +435,10 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.recon_radius = R;
   w.eps = prm->eps;
   w.has_extinction = c->has_extinction ? 1u : 0u;
-  w.fetch_threshold = c->fetch_threshold, w.postpone_lanes = c->postpone_lanes;
+  w.fetch_threshold = c->fetch_threshold;
+  // a postponed primitive group takes a second stack entry on its level: only trees of at most kMaxStack / 2 levels
+  // (8^16 leaves) leave room for that, deeper ones are walked without postponing
+  w.postpone_lanes = 2 * c->bvh_host_stats.depth <= (uint32_t)kMaxStack ? c->postpone_lanes : 0u;
   w.unresolved = c->d_unresolved.p;
   w.coop_batch_cost = c->coop_batch_cost;
   const bool exact = (prm->flags & HJK_RENDER_EXACT_TIES) != 0;
@@ -528,10 +530,9 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     if (stats) {
       unsigned long long totals[3] = {0, 0, 0};
       HJK_CUDA(c, cudaMemcpy(totals, c->d_totals.p, sizeof totals, cudaMemcpyDeviceToHost));
-      uint32_t unresolved[2] = {0, 0};
-      HJK_CUDA(c, cudaMemcpy(unresolved, c->d_unresolved.p, 8, cudaMemcpyDeviceToHost));
-      c->unresolved_last = unresolved[0];
-      c->stack_overflows += unresolved[1];
+      uint32_t unresolved = 0;
+      HJK_CUDA(c, cudaMemcpy(&unresolved, c->d_unresolved.p, 4, cudaMemcpyDeviceToHost));
+      c->unresolved_last = unresolved;
       n_paths = totals[0], n_ext = totals[1], n_sh = totals[2];
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -947,7 +948,6 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   d.camera = info->camera;
   for (int k = 0; k < 4; k++) d.sph_centre[k] = bvh.sph_centre[k];
   d.sph_rmin = bvh.sph_rmin, d.sph_rmax = bvh.sph_rmax;
-  d.postpone_limit = bvh.depth < (uint32_t)kMaxStack ? (uint32_t)kMaxStack - bvh.depth : 0u;
   c->has_extinction = has_ext;
   if (keep) *keep = bvh;  // (empty vectors after a GPU build: the other devices of a group then build their own)
   bvh.nodes.clear();
@@ -955,7 +955,10 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   bvh.prims.clear();
   bvh.prims.shrink_to_fit();
   c->bvh_host_stats = bvh;
-  c->stack_overflows = 0;
+  {
+    const unsigned int zero = 0;
+    HJK_CUDA(c, cudaMemcpyToSymbol(g_stack_overflows, &zero, sizeof zero));
+  }
   c->has_scene = true;
   return HJK_OK;
 }
@@ -1277,16 +1280,18 @@ int hjk_trace_first_hit_eps(HjkContext* c, const HjkRay* rays, uint64_t n_rays, 
   HJK_CUDA(c, d_o.ensure(n));
   HJK_CUDA(c, d_d.ensure(n));
   HJK_CUDA(c, d_h.ensure(n));
-  HJK_CUDA(c, d_cur.ensure(3));  // work cursor, unresolved tie clusters, stack overflows
+  HJK_CUDA(c, d_cur.ensure(2));  // work cursor, unresolved tie clusters
   HJK_CUDA(c, cudaMemcpyAsync(d_o.p, ho.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
   HJK_CUDA(c, cudaMemcpyAsync(d_d.p, hd.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
-  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 12, c->stream));
+  HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 8, c->stream));
   const int g = grid_for(c, c->blocks_trav);
   const bool guard = c->scene.num_spheres != 0;
   const uint32_t flavour = (any_hit & 1) ? kAnyHitBit : 0u;
   const bool exact = (any_hit & 2) != 0;
+  const int postpone = 2 * c->bvh_host_stats.depth <= (uint32_t)kMaxStack ? kPostponeLanes : 0;  // see render_blocks
 #define HJK_BATCH(G, E) \
-  k_trace_batch<G, E><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour)
+  k_trace_batch<G, E><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour, \
+                                                         postpone)
   if (guard && exact)
     HJK_BATCH(true, true);
   else if (guard)
@@ -1299,11 +1304,10 @@ int hjk_trace_first_hit_eps(HjkContext* c, const HjkRay* rays, uint64_t n_rays, 
   HJK_CUDA(c, cudaGetLastError());
   std::vector<f4>& hh = ho;  // the origins are on the device by now (same stream): reuse as the result buffer
   HJK_CUDA(c, cudaMemcpyAsync(hh.data(), d_h.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
-  uint32_t cur3[3] = {0, 0, 0};
-  HJK_CUDA(c, cudaMemcpyAsync(cur3, d_cur.p, 12, cudaMemcpyDeviceToHost, c->stream));
+  uint32_t cur2[2] = {0, 0};
+  HJK_CUDA(c, cudaMemcpyAsync(cur2, d_cur.p, 8, cudaMemcpyDeviceToHost, c->stream));
   HJK_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->unresolved_last = cur3[1];
-  c->stack_overflows += cur3[2];
+  c->unresolved_last = cur2[1];
   for (size_t i = 0; i < n; i++) {
     int32_t id;
     memcpy(&id, &hh[i].x, 4);
@@ -1523,7 +1527,13 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "bvh_builder") *out = c->bvh_builder;
   else if (k == "bvh_build_us") *out = (int64_t)(c->bvh_build_ms * 1000.f);
   else if (k == "unresolved_ties") *out = (int64_t)c->unresolved_last;
-  else if (k == "stack_overflows") *out = (int64_t)c->stack_overflows;
+  else if (k == "stack_overflows") {  // entries the traversal stack dropped on this device since the last scene upload
+    unsigned int v = 0;
+    HJK_CUDA(c, cudaSetDevice(c->device));
+    HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+    HJK_CUDA(c, cudaMemcpyFromSymbol(&v, g_stack_overflows, sizeof v));
+    *out = (int64_t)v;
+  }
   else if (k == "device") *out = c->device;
   else if (k == "n_devices") *out = c->members.empty() ? 1 : (int64_t)c->members.size();
   else if (k == "rank") *out = c->rank;

@@ -70,8 +70,7 @@ struct WaveDev {
   uint32_t fetch_threshold;      // refill a warp when fewer lanes than this are busy
   uint32_t postpone_lanes;       // postpone primitive tests that fewer lanes than this would run
   uint32_t coop_batch_cost;      // pooled primitive tests: assumed instructions per batch of 32 (0 = always pool)
-  uint32_t* unresolved;          // [0] exact-tie mode: rays whose tie cluster outgrew the window/list;
-                                 // [1] traversal-stack entries that did not fit (must stay 0)
+  uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
 };
 
 #ifndef HJK_TRACE_COOP_MIN_BLOCKS
@@ -185,12 +184,14 @@ __global__ void __launch_bounds__(kTileThreads) k_raygen(WaveDev w) {
 }
 
 // ---------------------------------------------------------------- traversal
+// Traversal-stack entries that did not fit (a lost entry can lose a hit): hjk_scene_upload refuses trees that could
+// get here, so this stays 0; it is a module-level counter (no pointer to carry through the traversal loop, whose
+// register budget is spent) read by hjk_get_info("stack_overflows").
+__device__ unsigned int g_stack_overflows;
 struct DevStack {
   uint2* sm;  // this thread's column of the shared-memory stack (stride kTravThreads)
   uint2 local[kLocalStack];
   int n;
-  uint32_t* overflow;  // device counter: entries that did not fit (a lost entry can lose a hit: reported, see
-                       // hjk_get_info("stack_overflows"); hjk_scene_upload refuses trees that could get here)
   __device__ __forceinline__ int size() const { return n; }
   __device__ __forceinline__ void push(uint32_t a, uint32_t b) {
     if (n < kSmStack) {
@@ -198,7 +199,7 @@ struct DevStack {
     } else if (n < kMaxStack) {
       local[n - kSmStack] = make_uint2(a, b);
     } else {
-      atomicAdd(overflow, 1u);
+      atomicAdd(&g_stack_overflows, 1u);
     }
     n++;
   }
@@ -283,7 +284,6 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
   DevStack st;
   st.sm = sm_stack + threadIdx.x;
   st.n = 0;
-  st.overflow = unresolved + 1;
   TravState s;
   typename std::conditional<EXACT, TieCands, NoCands>::type cands;
   cands.reset();
@@ -332,8 +332,7 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 // The exact-tie mode keeps the per-lane loop (it must record every candidate).
 template <int GUARD, class IO>
 __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO& io, uint32_t n, uint32_t* cursor,
-                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost,
-                                                    uint32_t* unresolved) {
+                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost) {
   __shared__ uint2 sm_stack[kSmStack * kTravThreads];
   __shared__ unsigned long long sm_best[kTravThreads];
   const uint32_t lane = threadIdx.x & 31u;
@@ -341,7 +340,6 @@ __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO
   DevStack st;
   st.sm = sm_stack + threadIdx.x;
   st.n = 0;
-  st.overflow = unresolved + 1;
   TravState s;
   s.tg_y = 0, s.ng_y = 0;
   bool active = false, exhausted = false;
@@ -519,15 +517,15 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_COOP_MIN_B
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
   const WaveIO io{w, w.ray_o[bounce & 1u], w.ray_d[bounce & 1u], n_shadow};
   traverse_queue_coop<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
-                             w.coop_batch_cost, w.unresolved);
+                             w.coop_batch_cost);
 }
-// cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode), cursor[2] = stack overflows
+// cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode)
 template <int GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
                                                               f4* hit, uint32_t n, uint32_t* cursor, float eps,
-                                                              uint32_t flavour) {
+                                                              uint32_t flavour, int postpone_lanes) {
   const BatchIO io{sc, ray_o, ray_d, hit, flavour};
-  traverse_queue<GUARD, EXACT>(sc, io, n, cursor, eps, kFetchThreshold, kPostponeLanes, cursor + 1);
+  traverse_queue<GUARD, EXACT>(sc, io, n, cursor, eps, kFetchThreshold, postpone_lanes, cursor + 1);
 }
 
 // ---------------------------------------------------------------- sort + shade

@@ -60,9 +60,6 @@ struct SceneDev {
   // traversal's sphere guard (traverse.cuh)
   float sph_centre[4];
   float sph_rmin, sph_rmax;
-  // primitive postponing (trav_run) may only push while the stack holds fewer entries than this: the stack
-  // capacity minus the tree depth, so the one-per-level node-group entries always still fit
-  uint32_t postpone_limit;
 };
 
 }  // namespace hjk

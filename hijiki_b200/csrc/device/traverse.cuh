@@ -378,7 +378,9 @@ struct TravNoPolicy {
 // the primitive loop: when it says yes and the lane still has inner-node work, the pending
 // primitives go to the stack and are tested later, when more lanes of the warp have primitive work
 // (only the visiting order changes, never what is accepted).
-//   Stack: push(uint32_t, uint32_t), pop(uint32_t&, uint32_t&), empty(), size().
+//   Stack: push(uint32_t, uint32_t), pop(uint32_t&, uint32_t&), empty().  A postponed primitive group takes a
+//   stack entry on top of the one node-group entry per level: callers whose stack holds fewer than two entries
+//   per tree level must use a policy that never postpones (hjk_scene_upload does: see postpone_lanes).
 // Any-hit rays (top bit of s.slot set) return at the first accepted primitive.
 // EXACT: closest-hit rays record their candidates in `cands` (TieCands) and resolve ties at the end.
 template <int GUARD, bool EXACT, class Stack, class Policy, class Cands>
@@ -403,7 +405,7 @@ HJK_HD bool trav_run(const SceneDev& sc, TravState& s, Stack& stack, float eps, 
       s.ng_x = s.ng_y = 0;
     }
     while (s.tg_y) {
-      if (s.ng_y > 0x00FFFFFFu && (uint32_t)stack.size() < sc.postpone_limit && policy.postpone()) {
+      if (s.ng_y > 0x00FFFFFFu && policy.postpone()) {
         stack.push(s.tg_x, s.tg_y);
         break;
       }

@@ -7,11 +7,13 @@
 #include "hijiki_oracle.h"
 #include "orc_math.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -105,6 +107,7 @@ struct SceneView {
   const Vec4* dielectricMaterials;  // extinction_etaRatio
   const Vec4* emissiveMaterials;    // vec3 power (16 B stride)
   int numSpheres, numQuads, numTriangles, numEmitters;
+  const struct CullAccel* accel = nullptr;  // mode 3 only (see CullAccel)
 };
 
 SceneView make_view(const OrcScene* s) {
@@ -408,8 +411,199 @@ bool intersectShape(const SceneView& s, const Ray& ray, uint32_t shapeIndex, Int
   return intersectTriangle(s, ray, shapeIndex - s.numSpheres - s.numQuads, its);
 }
 
+// ------------------------------------------------------------------ mode 3: culled linear scan (oracle extension)
+// The reference's linear scan (scene.glsl:134-157, mode 2 = without the >100 failsafe) costs one primitive test
+// per primitive per ray: minutes for one 1080p pass of cbox, hours for the 10 M-triangle terrain.  Mode 3 runs
+// THE SAME SCAN — ascending shape index, tMax = t - M_EPS after every accepted hit — over a subset of the
+// primitives: those whose bounding box, padded, the ray's supporting half-line pierces.  A primitive outside
+// that subset cannot be accepted by its test (an accepted hit lies on the primitive, hence inside its box), so
+// dropping it changes nothing: same winner, same t, same order dependence among ties.  The subset comes from
+// an oracle-private median-split box tree over the primitives' own boxes; the slab test runs in double
+// precision against boxes padded by 1e-4 of the scene scale, and ignores the ray's tMin/tMax altogether.
+// Two cases are kept out of the culling because the reference's arithmetic is not geometric there:
+//   * spheres are only culled for directions of unit length within 1e-4 and origins inside the padded scene
+//     bounds; their boxes carry the extra radius R' - r of shapes/sphere.glsl's non-unit-direction behaviour
+//     (see traverse.cuh "SPHERE GUARD" for the algebra); any other ray tests every sphere;
+//   * a direction exactly perpendicular to a triangle's normal makes triangle.glsl:24 divide by zero and can
+//     report t = +inf "hits": such artefact hits (never produced by integrator rays) are not reproduced.
+// tests/test_oracle_cull.py holds mode 3 identical to modes 0/2 (ids, t, uv, tie flags, whole frames).
+struct CullAccel {
+  struct Node {
+    double lo[3], hi[3];
+    uint32_t left, right;   // children (inner) ...
+    uint32_t first, count;  // ... or a range of `order` (leaf: count > 0)
+  };
+  std::vector<Node> nodes;
+  std::vector<uint32_t> order;  // global shape ids
+  double lo[3], hi[3];          // padded bounds of every primitive and the camera
+  int numSpheres = 0;
+};
+
+struct PrimBox {
+  double lo[3], hi[3], c[3];
+};
+
+inline void box_grow(double* lo, double* hi, double x, double y, double z) {
+  const double p[3] = {x, y, z};
+  for (int k = 0; k < 3; k++) {
+    if (p[k] < lo[k]) lo[k] = p[k];
+    if (p[k] > hi[k]) hi[k] = p[k];
+  }
+}
+
+std::shared_ptr<CullAccel> build_cull_accel(const SceneView& s) {
+  auto acc = std::make_shared<CullAccel>();
+  const int total = s.numSpheres + s.numQuads + s.numTriangles;
+  acc->numSpheres = s.numSpheres;
+  std::vector<PrimBox> boxes((size_t)total);
+  double slo[3] = {1e300, 1e300, 1e300}, shi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < total; i++) {
+    PrimBox& b = boxes[(size_t)i];
+    for (int k = 0; k < 3; k++) b.lo[k] = 1e300, b.hi[k] = -1e300;
+    if (i < s.numSpheres) {
+      const Sphere& sp = s.spheres[i];
+      const double r = std::fabs((double)sp.positionRadius[3]);
+      box_grow(b.lo, b.hi, sp.positionRadius[0] - r, sp.positionRadius[1] - r, sp.positionRadius[2] - r);
+      box_grow(b.lo, b.hi, sp.positionRadius[0] + r, sp.positionRadius[1] + r, sp.positionRadius[2] + r);
+    } else if (i < s.numSpheres + s.numQuads) {
+      const Quad& q = s.quads[i - s.numSpheres];
+      for (int a = 0; a < 2; a++)
+        for (int c = 0; c < 2; c++)
+          box_grow(b.lo, b.hi, (double)q.origin[0] + a * (double)q.edge1[0] + c * (double)q.edge2[0],
+                   (double)q.origin[1] + a * (double)q.edge1[1] + c * (double)q.edge2[1],
+                   (double)q.origin[2] + a * (double)q.edge1[2] + c * (double)q.edge2[2]);
+    } else {
+      const uint32_t t = (uint32_t)(i - s.numSpheres - s.numQuads);
+      for (int v = 0; v < 3; v++) {
+        const Vertex& vx = s.vertices[s.triangles[3 * t + v]];
+        box_grow(b.lo, b.hi, vx.pos_u[0], vx.pos_u[1], vx.pos_u[2]);
+      }
+    }
+    for (int k = 0; k < 3; k++) {
+      b.c[k] = 0.5 * (b.lo[k] + b.hi[k]);
+      if (b.lo[k] < slo[k]) slo[k] = b.lo[k];
+      if (b.hi[k] > shi[k]) shi[k] = b.hi[k];
+    }
+  }
+  box_grow(slo, shi, s.info->camera.position[0], s.info->camera.position[1], s.info->camera.position[2]);
+  double scale = 0.0;
+  for (int k = 0; k < 3; k++) scale = std::max(scale, std::max(std::fabs(slo[k]), std::fabs(shi[k])));
+  const double pad = 1e-4 * scale + 1e-7;
+  double diag2 = 0.0;
+  for (int k = 0; k < 3; k++) {
+    acc->lo[k] = slo[k] - 2 * pad, acc->hi[k] = shi[k] + 2 * pad;
+    diag2 += (acc->hi[k] - acc->lo[k]) * (acc->hi[k] - acc->lo[k]);
+  }
+  for (int i = 0; i < total; i++) {
+    double extra = pad;
+    if (i < s.numSpheres) {  // R' - r <= eps (r^2 + L^2) / (2 r) for |s^2 - 1| <= eps = 1e-4, L <= scene diagonal; x 2
+      const double r = std::max(std::fabs((double)s.spheres[i].positionRadius[3]), 1e-30);
+      extra += 2.0 * 1e-4 * (r * r + diag2) / (2.0 * r);
+    }
+    for (int k = 0; k < 3; k++) boxes[(size_t)i].lo[k] -= extra, boxes[(size_t)i].hi[k] += extra;
+  }
+  acc->order.resize((size_t)total);
+  for (int i = 0; i < total; i++) acc->order[(size_t)i] = (uint32_t)i;
+  // median split on the longest axis of the centroid bounds, leaves of <= 4 primitives; the big ranges near the
+  // root are split on their own threads (node slots come from an atomic counter, so the tree does not depend on
+  // scheduling in anything but node numbering, which nothing reads)
+  acc->nodes.resize((size_t)std::max(total, 1) * 2);
+  std::atomic<uint32_t> next_node{1};
+  std::function<void(uint32_t, uint32_t, uint32_t, int)> build = [&](uint32_t node, uint32_t first, uint32_t count,
+                                                                      int par_depth) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t k = first; k < first + count; k++) {
+      const PrimBox& b = boxes[acc->order[k]];
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(lo[a], b.lo[a]), hi[a] = std::max(hi[a], b.hi[a]);
+        clo[a] = std::min(clo[a], b.c[a]), chi[a] = std::max(chi[a], b.c[a]);
+      }
+    }
+    CullAccel::Node n{};
+    for (int a = 0; a < 3; a++) n.lo[a] = lo[a], n.hi[a] = hi[a];
+    if (count <= 4) {
+      n.first = first, n.count = count;
+      acc->nodes[node] = n;
+      return;
+    }
+    int axis = 0;
+    for (int a = 1; a < 3; a++)
+      if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+    const uint32_t half = count / 2;
+    std::nth_element(acc->order.begin() + first, acc->order.begin() + first + half, acc->order.begin() + first + count,
+                     [&](uint32_t x, uint32_t y) {
+                       const double cx = boxes[x].c[axis], cy = boxes[y].c[axis];
+                       return cx < cy || (cx == cy && x < y);
+                     });
+    n.left = next_node.fetch_add(2);
+    n.right = n.left + 1;
+    n.count = 0;
+    acc->nodes[node] = n;
+    if (par_depth > 0 && count > (1u << 16)) {
+      std::thread t(build, n.left, first, half, par_depth - 1);
+      build(n.right, first + half, count - half, par_depth - 1);
+      t.join();
+    } else {
+      build(n.left, first, half, 0);
+      build(n.right, first + half, count - half, 0);
+    }
+  };
+  if (total > 0) build(0u, 0u, (uint32_t)total, 4);
+  acc->nodes.resize(next_node.load());
+  return acc;
+}
+
+// shape ids (ascending) the mode-3 scan has to test for this ray
+void cull_candidates(const CullAccel& a, const Ray& ray, std::vector<uint32_t>& out) {
+  out.clear();
+  const double o[3] = {ray.origin.x, ray.origin.y, ray.origin.z};
+  const double d[3] = {ray.direction.x, ray.direction.y, ray.direction.z};
+  const double s2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  bool cull_spheres = std::fabs(s2 - 1.0) <= 1e-4;
+  for (int k = 0; k < 3; k++)
+    if (!(o[k] >= a.lo[k] && o[k] <= a.hi[k])) cull_spheres = false;
+  if (!cull_spheres)
+    for (int i = 0; i < a.numSpheres; i++) out.push_back((uint32_t)i);
+  const double t_lo = ray.tMin < 0.f ? -1e300 : 0.0;  // the half-line ahead of the origin (the whole line if tMin < 0)
+  uint32_t stack[128];
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp) {
+    const CullAccel::Node& n = a.nodes[stack[--sp]];
+    double t0 = t_lo, t1 = 1e300;
+    bool miss = false;
+    for (int k = 0; k < 3 && !miss; k++) {
+      if (d[k] == 0.0) {
+        if (o[k] < n.lo[k] || o[k] > n.hi[k]) miss = true;
+      } else {
+        double ta = (n.lo[k] - o[k]) / d[k], tb = (n.hi[k] - o[k]) / d[k];
+        if (ta > tb) std::swap(ta, tb);
+        // one part in 1e9 of slack: the divisions round
+        ta -= 1e-9 * std::fabs(ta), tb += 1e-9 * std::fabs(tb);
+        if (ta > t0) t0 = ta;
+        if (tb < t1) t1 = tb;
+        if (t0 > t1) miss = true;
+      }
+    }
+    if (miss) continue;
+    if (n.count) {
+      for (uint32_t k = n.first; k < n.first + n.count; k++) {
+        const uint32_t id = a.order[k];
+        if (!cull_spheres && (int)id < a.numSpheres) continue;  // already listed
+        out.push_back(id);
+      }
+    } else if (sp + 2 <= 128) {
+      stack[sp++] = n.left;
+      stack[sp++] = n.right;
+    }
+  }
+  std::sort(out.begin(), out.end());
+}
+
 // mode: 0 = USE_BVH 0 (linear scan incl. the >100 failsafe), 1 = USE_BVH 1, 2 = linear scan
-// without the failsafe (oracle extension for scenes the reference refuses)
+// without the failsafe (oracle extension for scenes the reference refuses), 3 = the scan of mode 2 over
+// the primitives whose box the ray pierces (CullAccel above; same results, tractable at BASELINE sizes)
 bool intersectScene(const SceneView& s, int useBvh, float M_EPS, Ray ray, Intersection& its) {
   // scene.glsl:97-175
   its.objectID = -1;
@@ -441,6 +635,16 @@ bool intersectScene(const SceneView& s, int useBvh, float M_EPS, Ray ray, Inters
         } else {
           currentNode = exitIndex;
         }
+      }
+    }
+  } else if (useBvh == 3) {
+    // scene.glsl:139-157 over the culled subset, in the same (ascending shape index) order
+    thread_local std::vector<uint32_t> cands;
+    cull_candidates(*s.accel, ray, cands);
+    for (uint32_t id : cands) {
+      if (intersectShape(s, ray, id, its)) {
+        ray.tMax = its.t - M_EPS;
+        its.objectID = (int)id;
       }
     }
   } else {
@@ -861,8 +1065,11 @@ int orc_trace(const OrcScene* scene, const OrcRay* rays, uint64_t n, int use_bvh
   if (!scene || !rays || !shape_id) return -1;
   SceneView s = make_view(scene);
   if (use_bvh == 1 && (!s.bvh || s.bvhLength == 0)) return -2;
+  std::shared_ptr<CullAccel> accel;
+  if (use_bvh == 3) accel = build_cull_accel(s), s.accel = accel.get();
   n_threads = default_threads(n_threads);
   parallel_for(n, n_threads, [&](uint64_t b, uint64_t e, int) {
+    std::vector<uint32_t> subset;
     for (uint64_t i = b; i < e; i++) {
       Ray ray{V(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]),
               V(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]), rays[i].t_min,
@@ -879,10 +1086,15 @@ int orc_trace(const OrcScene* scene, const OrcRay* rays, uint64_t n, int use_bvh
           // candidates of every primitive in the ORIGINAL interval; tie if the winner is
           // test-order dependent
           int total = s.numSpheres + s.numQuads + s.numTriangles;
+          if (use_bvh == 3) {  // only primitives of the culled subset can be hit at all
+            cull_candidates(*s.accel, ray, subset);
+            total = (int)subset.size();
+          }
           float tP = INFINITY;
           int P = -1;
           std::vector<std::pair<int, float>> cands;
-          for (int k = 0; k < total; k++) {
+          for (int kk = 0; kk < total; kk++) {
+            const int k = use_bvh == 3 ? (int)subset[(size_t)kk] : kk;
             Intersection tmp{};
             if (intersectShape(s, ray, (uint32_t)k, tmp)) {
               cands.emplace_back(k, tmp.t);
@@ -922,6 +1134,8 @@ int orc_occluded(const OrcScene* scene, const OrcRay* rays, uint64_t n, int use_
   if (!scene || !rays || !occluded) return -1;
   SceneView s = make_view(scene);
   if (use_bvh == 1 && (!s.bvh || s.bvhLength == 0)) return -2;
+  std::shared_ptr<CullAccel> accel;
+  if (use_bvh == 3) accel = build_cull_accel(s), s.accel = accel.get();
   n_threads = default_threads(n_threads);
   parallel_for(n, n_threads, [&](uint64_t b, uint64_t e, int) {
     for (uint64_t i = b; i < e; i++) {
@@ -940,6 +1154,8 @@ int orc_integrate_frame(const OrcScene* scene, const OrcBlock* blocks, uint64_t 
   if (!scene || !blocks || !p || !layers || n_blocks == 0) return -1;
   SceneView s = make_view(scene);
   if (p->use_bvh == 1 && (!s.bvh || s.bvhLength == 0)) return -2;
+  std::shared_ptr<CullAccel> accel;
+  if (p->use_bvh == 3) accel = build_cull_accel(s), s.accel = accel.get();
   n_threads = default_threads(n_threads);
   const uint32_t W = blocks[0].original_dimension[0], H = blocks[0].original_dimension[1];
   const uint64_t plane = (uint64_t)W * H * 4;
@@ -1016,6 +1232,8 @@ int orc_render(const OrcScene* scene, const OrcBlock* blocks, uint64_t n_blocks,
   if (!scene || !blocks || !p || !accumulator || n_blocks == 0) return -1;
   SceneView s = make_view(scene);
   if (p->use_bvh == 1 && (!s.bvh || s.bvhLength == 0)) return -2;
+  std::shared_ptr<CullAccel> accel;
+  if (p->use_bvh == 3) accel = build_cull_accel(s), s.accel = accel.get();
   n_threads = default_threads(n_threads);
   const uint32_t bs = p->block_size ? p->block_size : 128;
   // intermediate texture: bs x bs x 3 layers RGBA32F, persistent across blocks
@@ -1081,6 +1299,8 @@ int orc_trace_path(const OrcScene* scene, const OrcBlock* block, uint32_t lx, ui
   c.M_EPS = p->eps;
   c.useBvh = (int)p->use_bvh;
   if (c.useBvh == 1 && (!c.s.bvh || c.s.bvhLength == 0)) return -2;
+  std::shared_ptr<CullAccel> accel;
+  if (c.useBvh == 3) accel = build_cull_accel(c.s), c.s.accel = accel.get();
   PathOut o;
   int n = 0;
   renderPixel(c, *block, lx, ly, *p, o, out, capacity, &n);

@@ -54,7 +54,10 @@ typedef struct OrcParams {
   uint32_t recon_radius;
   float recon_stddev;
   float eps;            /* math.glsl:2 */
-  uint32_t use_bvh;     /* scene.glsl USE_BVH: 0 = linear scan (reference default), 1 = threaded BVH2 */
+  uint32_t use_bvh;     /* scene.glsl USE_BVH: 0 = linear scan (reference default), 1 = threaded BVH2;
+                           oracle extensions: 2 = linear scan without the >100-shape failsafe, 3 = the scan of
+                           mode 2 over the primitives whose box the ray pierces (same results, tractable at
+                           BASELINE sizes; hijiki_oracle.cpp "mode 3") */
   uint32_t block_size;  /* intermediate texture edge, src/main.rs:1197-1201 (128) */
   uint32_t skip_recon;
 } OrcParams;

@@ -32,7 +32,6 @@ struct HostStack {
     a = data[2 * n], b = data[2 * n + 1];
   }
   bool empty() const { return n == 0; }
-  int size() const { return n; }
 };
 
 // Scheduling stress: postpones and yields on a fixed pseudo-random pattern, so the resumable state
@@ -137,7 +136,6 @@ void* ht_create(const HjkScene* s, float pad_rel, char* err_out, int err_cap) {
   sc.camera = info->camera;
   for (int k = 0; k < 4; k++) sc.sph_centre[k] = h->bvh.sph_centre[k];
   sc.sph_rmin = h->bvh.sph_rmin, sc.sph_rmax = h->bvh.sph_rmax;
-  sc.postpone_limit = h->bvh.depth < 32u ? 32u - h->bvh.depth : 0u;  // as hjk_scene_upload sets it (32-entry stack)
   return h;
 }
 void ht_destroy(void* p) { delete (Harness*)p; }
