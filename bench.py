@@ -13,8 +13,9 @@ into it and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectSce
   value      device-resident throughput: the step's block list already lives in HBM; timed with
              CUDA events on the stream the kernels run on, max over ranks.
   e2e        the same step through the public call (`hjk_render` with a HOST block list in pinned
-             memory + `hjk_readback` of the normalised frame to pinned host memory), copies in the
-             timed region.
+             memory + `hjk_readback_root` of the normalised frame to pinned host memory), copies in the
+             timed region.  N > 1: the library's own communicator (hjk_comm_init, bootstrapped over the
+             torchrun rendezvous) sums the frames with one ncclReduce to rank 0, which alone reads back.
   roofline   the dominant kernel (k_trace_coop, BVH traversal of extension + shadow rays): algorithmic
              bytes it must move per ray / its average launch time, against the measured HBM copy peak.
   cpu_baseline / --impl reference
@@ -22,9 +23,11 @@ into it and — for N > 1 — all-reduced over NCCL.  One RAY = one intersectSce
              reference's --use-bvh), on all host cores, on a bounded sample of the same workload.
              The reference's own wgpu/lavapipe path cannot run in this image.
 
-Other workloads (`--workload`): cbox_default (configs[0]), terrain (configs[2], 10 M triangles),
-spheres (configs[3], 512 dielectric/mirror spheres at 3840x2160; spheres64 = the same with max 64 bounces); configs[4] (reconstruction on
-3840x2160 feature buffers) is the `denoiser` object of every line.
+The default line also carries, as objects measured the same way (fewer steps), the other configs of
+BASELINE.json: `terrain` (configs[2], 10 M triangles), `spheres` (configs[3], 512 dielectric/mirror spheres at
+3840x2160; `spheres64` = the same with max 64 bounces), `denoiser` (configs[4], reconstruction on 3840x2160
+feature buffers), and `strong`: a fixed 256-spp cbox 1080p job split over the N GPUs, timed from scene upload
+(BVH built once, broadcast) to the frame on rank 0's host.  `--workload NAME` makes one of them the main line.
 """
 from __future__ import annotations
 
@@ -59,10 +62,38 @@ EXTEND_BYTES_PER_RAY = 4 + 32 + 16
 SHADOW_BYTES_PER_RAY = 32 + 16
 PIPE_BYTES_EXT, PIPE_BYTES_SHADOW = 192, 96
 RECON_BYTES_PER_PX = 64  # 2 x 16 B layers + accumulator read + write (the all-zero albedo layer is elided)
-# dram__bytes_read.sum + dram__bytes_write.sum of k_trace_coop per traced ray, from the ncu --set full capture of
-# one whole wave in profiles/r01f_ncu_full_wave_selected.csv (14.59 GB over its nine k_trace_coop launches,
-# 216.3 M rays; 17.58 GB = 81.3 B/ray before the path state became queue-ordered)
-TRACE_DRAM_BYTES_PER_RAY_NCU = 67.5
+SCENE_FETCH_BYTES_PER_RAY = 784  # uncached lower bound for scenes exceeding L2 (terrain): 8 nodes x 80 + 3 x 48
+NCU_METRICS = os.path.join(ROOT, "profiles", "ncu_trace_metrics.json")
+KERNEL_SOURCES = ("kernels.cuh", "traverse.cuh", "shade.cuh", "recon.cuh", "hjk_math.cuh", "scene_dev.cuh")
+
+
+def kernel_source_sha() -> str:
+    """Digest of the device sources the ncu-derived figures belong to."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "hijiki_b200", "csrc", "device", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_metrics(kind: str):
+    """Figures that only a profiler can give (DRAM bytes per traced ray, issue-active cycles, lanes per instruction of
+    the trace kernel), read from the committed summary of the ncu capture — written by tools/ncu_trace_metrics.py from
+    the capture's raw page — never hard-coded here.  `stale` says the device sources changed since the capture."""
+    try:
+        with open(NCU_METRICS) as f:
+            m = json.load(f)
+    except Exception:
+        return None
+    e = m.get("workloads", {}).get(kind)
+    if not e:
+        return None
+    e = dict(e)
+    e["source"] = m.get("source")
+    e["kernel_source_sha"] = m.get("kernel_source_sha")
+    e["stale"] = m.get("kernel_source_sha") != kernel_source_sha()
+    return e
 
 
 def measured_peaks():
@@ -142,31 +173,48 @@ def step_slice(blocks, bpp, step, rank, world, spp_per_step):
 
 
 # ------------------------------------------------------------------------------ CPU arm
+# Self-contained: scene arrays, the reference-layout BVH2 and the block list come from the TESTS-side build of the
+# host front-end (tests/native/libhjk_hosttest.so), the path tracer is oracle/liboracle.so.  The product's
+# libhijiki_b200.so is never loaded by this arm.
+def _host_scene(_libs, kind):
+    H = _libs.hosttest()
+    if kind == "cbox":
+        return _libs.HostScene.from_obj(H, CBOX, put_spheres=False, with_bvh2=True)
+    if kind == "terrain":
+        return _libs.HostScene.terrain(H, 2237, with_bvh2=False)
+    if kind == "spheres":
+        return _libs.HostScene.spheres(H, 8, with_bvh2=True)
+    raise KeyError(kind)
+
+
 def _oracle_setup(wl):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _libs
-    import hijiki_b200 as hj
     label, kind, width, height, spp, max_bounces, _ = wl
     O = _libs.oracle()
     cores = O.orc_hardware_threads()
-    compiled = make_scene(kind).compile(use_bvh=True)
-    gen = hj.ImageBlockGenerator(width, height, BLOCK, spp)
+    scene = _host_scene(_libs, kind)
     # bounded block list: never materialise millions of blocks for the CPU arm
-    gen.num_samples = min(spp, 64)
-    blocks = gen.blocks()
-    op = _libs.orc_params(max_bounces=max_bounces, use_bvh=1, block_size=BLOCK)
+    blocks = _libs.generate_blocks(_libs.hosttest(), width, height, min(spp, 64), BLOCK)
+    bpp = ((width + BLOCK - 1) // BLOCK) * ((height + BLOCK - 1) // BLOCK)
+    # threaded BVH2 = what the reference's --use-bvh walks; the 10 M-triangle terrain cannot be represented in that
+    # layout (exit sentinel 1000000, src/main.rs:231): it runs the oracle's culled linear scan instead
+    mode = 3 if kind == "terrain" else 1
+    op = _libs.orc_params(max_bounces=max_bounces, use_bvh=mode, block_size=BLOCK)
     acc = np.zeros((height, width, 4), np.float32)
 
     def run(sample):
         st = _libs.OrcStats()
         t0 = time.perf_counter()
-        rc = O.orc_render(C.byref(compiled.view), _libs.ptr(sample), sample.size, C.byref(op), _libs.ptr(acc),
+        rc = O.orc_render(C.byref(scene.view), _libs.ptr(sample), sample.size, C.byref(op), _libs.ptr(acc),
                           C.byref(st), cores)
         dt = time.perf_counter() - t0
         assert rc == 0
         return st.n_extension_rays + st.n_shadow_rays, dt
 
-    return run, blocks, gen.blocks_per_pass, cores
+    how = ("oracle, culled linear scan (mode 3): the reference's BVH layout cannot hold 10 M triangles" if mode == 3
+           else "oracle, threaded-BVH2 mode = reference --use-bvh")
+    return run, blocks, bpp, cores, how
 
 
 def run_reference(args, rank, wl):
@@ -177,12 +225,7 @@ def run_reference(args, rank, wl):
     base = {"impl": "reference", "metric": "Mrays/s (all bounces)", "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
-    if kind == "terrain":
-        base["unavailable"] = ("the reference's flattened BVH uses exit index 1000000 as its end sentinel "
-                               "(src/main.rs:231) and cannot represent a 10 M-triangle scene")
-        emit(base)
-        return
-    run, blocks, bpp, cores = _oracle_setup(wl)
+    run, blocks, bpp, cores, how = _oracle_setup(wl)
     mid = bpp // 2
     _, dt = run(blocks[mid:mid + 2])  # calibrate on two blocks from the middle of the frame
     per_block = max(dt / 2, 1e-4)
@@ -200,8 +243,8 @@ def run_reference(args, rank, wl):
     sample = f"{nb} ImageBlocks ({nb / bpp:.2f} sample passes of {width}x{height}) per step"
     base.update({
         "value": value, "ms_per_step": tot_dt / args.steps * 1e3,
-        "config": {"workload": label, "note": "CPU restatement of reference GLSL (threaded-BVH2 mode = reference "
-                   f"--use-bvh), {cores} host threads — the reference's wgpu/lavapipe path cannot run in this image"},
+        "config": {"workload": label, "note": f"CPU restatement of reference GLSL ({how}), {cores} host threads — the "
+                   "reference's wgpu/lavapipe path cannot run in this image"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,10 +255,7 @@ def run_reference(args, rank, wl):
 def cpu_baseline_sample(wl):
     """Bounded CPU sample for the main line (rank 0, N = 1): ~20 s of oracle work."""
     label, kind, width, height = wl[:4]
-    if kind == "terrain":
-        return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port",
-                "sample": "unavailable: the reference BVH layout cannot represent 10 M triangles (src/main.rs:231)"}
-    run, blocks, bpp, cores = _oracle_setup(wl)
+    run, blocks, bpp, cores, how = _oracle_setup(wl)
     mid = bpp // 2
     _, dt = run(blocks[mid:mid + 2])
     per_block = max(dt / 2, 1e-4)
@@ -223,7 +263,7 @@ def cpu_baseline_sample(wl):
     rays, dt = run(blocks[:nb])
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
             "sample": f"first {nb} ImageBlocks ({nb / bpp:.1f} sample passes of {width}x{height}) of the job, "
-                      f"{rays / 1e6:.1f} Mrays in {dt:.1f} s (oracle, threaded-BVH2 mode = reference --use-bvh)"}
+                      f"{rays / 1e6:.1f} Mrays in {dt:.1f} s ({how})"}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -250,6 +290,311 @@ def emit(obj):
         os.write(_RESULT_FD, line)
 
 
+class Rig:
+    """One rank's device state: the context on this rank's GPU, running on a torch stream, joined to the other ranks
+    through the LIBRARY's communicator (hjk_comm_unique_id / hjk_comm_init; the 128-byte id travels over the torchrun
+    rendezvous).  torch.distributed carries only the barrier and the gathering of the timings."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        import hijiki_b200 as hj
+        self.torch, self.dist, self.hj = torch, dist, hj
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        self.ctx = hj.Context(local_rank)
+        self.stream = torch.cuda.Stream(device=local_rank)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(hj.comm_unique_id()), dtype=torch.uint8).clone()
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            self.ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_over_ranks(self, values):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t)
+        return t.tolist()
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def run_workload(rig, wl, steps, warmup, sps, want_e2e, want_exact, sample_clocks):
+    """Times one workload on every rank.  Returns the merged (max time, summed rays) record on every rank."""
+    hj, torch = rig.hj, rig.torch
+    ctx, stream, rank, world = rig.ctx, rig.stream, rig.rank, rig.world
+    label, kind, width, height, spp, max_bounces, default_sps = wl
+    sps = sps or default_sps
+    n_steps_total = warmup + steps
+    gen = hj.ImageBlockGenerator(width, height, BLOCK, spp)
+    bpp = gen.blocks_per_pass
+    # only the passes the run touches are generated (the list is a prefix of the job's list)
+    gen.num_samples = min(spp, n_steps_total * sps * world)
+    blocks = gen.blocks()
+    t0 = time.perf_counter()
+    compiled = make_scene(kind).compile(use_bvh=False)
+    t_scene = time.perf_counter() - t0
+    rig.barrier()
+    t0 = time.perf_counter()
+    ctx.scene_upload(compiled)  # N > 1: rank 0 builds the wide BVH, ncclBroadcast carries it to the others
+    ctx.synchronize()
+    t_upload = time.perf_counter() - t0
+    ctx.frame_begin(width, height)
+    ctx.set_profiling(True)
+    params = hj.make_params(max_bounces=max_bounces)
+
+    def reduce():
+        if world > 1:
+            ctx.reduce_frame(0, timed=False)  # one ncclReduce(sum) of the W x H float4 frame to rank 0
+
+    # ---------------- device-resident arm: block lists uploaded before the timed region
+    slices = [step_slice(blocks, bpp, s, rank, world, sps) for s in range(n_steps_total)]
+    handles = [ctx.blocks_upload(s) for s in slices]
+    for s in range(warmup):
+        ctx.frame_begin(width, height)
+        ctx.render_resident(handles[s], 0, slices[s].size, params)
+        reduce()
+    rig.barrier()
+    sampler = ClockSampler(rig.local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = rig.event(), rig.event()
+    rays = ext_rays = sh_rays = launches = 0
+    kernel_ms = {}
+    ev0.record(stream)
+    for s in range(warmup, n_steps_total):
+        ctx.frame_begin(width, height)
+        st = ctx.render_resident(handles[s], 0, slices[s].size, params)
+        reduce()
+        rays += st.n_rays
+        ext_rays += st.n_extension_rays
+        sh_rays += st.n_shadow_rays
+        launches += st.n_launches + (1 if world > 1 else 0)
+        for k, v in st.kernel_ms.items():
+            kernel_ms[k] = kernel_ms.get(k, 0.0) + v
+    ev1.record(stream)
+    rig.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = ev0.elapsed_time(ev1)
+
+    # exact-tie mode (HJK_RENDER_EXACT_TIES), two steps: what bit-identity with the reference on every ray costs
+    exact = None
+    if want_exact:
+        exact_params = hj.make_params(max_bounces=max_bounces, flags=hj.HJK_RENDER_EXACT_TIES)
+        exact_rays, exact_ms = 0, 0.0
+        for s in range(warmup, min(n_steps_total, warmup + 2)):
+            ctx.frame_begin(width, height)
+            st = ctx.render_resident(handles[s], 0, slices[s].size, exact_params)
+            exact_rays += st.n_rays
+            exact_ms += st.ms_total
+        exact = {"value": exact_rays / (exact_ms * 1e-3) / 1e6 if exact_ms else None, "unit": "Mrays/s",
+                 "unresolved_clusters_last_step": ctx.get_info("unresolved_ties"),
+                 "note": "this rank, 2 steps, HJK_RENDER_EXACT_TIES (the mode whose frames the parity tests hold "
+                         "bit-identical to the oracle at these sizes, tests/test_gpu_fullsize.py); unresolved = tie clusters "
+                         "longer than the 8*M_EPS window or 12 candidates, counted, each can move one sample"}
+    for h in handles:
+        ctx.blocks_free(h)
+
+    # ---------------- end-to-end arm: host block list in, normalised frame out (on rank 0), every step
+    e2e_ms, e2e_rays, result_mean = None, 0, None
+    if want_e2e:
+        pinned_blocks = [torch.from_numpy(s.view(np.uint8).copy()).pin_memory() for s in slices]
+        out_host = torch.empty((height, width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+        def e2e_step(s):
+            ctx.frame_begin(width, height)
+            st = ctx.render((pinned_blocks[s].data_ptr(), slices[s].size), params)
+            ctx.readback_root_ptr(0, out_host.data_ptr() if rank == 0 else 0, width * 16, normalise=True)
+            return st.n_rays
+
+        for s in range(warmup):
+            e2e_step(s)
+        rig.barrier()
+        e0, e1 = rig.event(), rig.event()
+        e0.record(stream)
+        for s in range(warmup, n_steps_total):
+            e2e_rays += e2e_step(s)
+        e1.record(stream)
+        rig.barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        if rank == 0:
+            result_mean = float(out_host[..., :3].mean())
+
+    # the path's one collective, timed alone
+    reduce_info = None
+    if world > 1:
+        rig.barrier()
+        a0, a1 = rig.event(), rig.event()
+        reps = 20
+        out = {}
+        for name, root in (("reduce_to_root", 0), ("allreduce", -1)):
+            ctx.frame_begin(width, height)
+            ctx.reduce_frame(root, timed=False)
+            rig.barrier()
+            a0.record(stream)
+            for _ in range(reps):
+                ctx.frame_begin(width, height)  # a fresh frame each time: the library skips a repeated reduction
+                ctx.reduce_frame(root, timed=False)
+            a1.record(stream)
+            rig.barrier()
+            out[name] = a0.elapsed_time(a1) / reps
+        z0, z1 = rig.event(), rig.event()
+        z0.record(stream)
+        for _ in range(reps):
+            ctx.frame_begin(width, height)
+        z1.record(stream)
+        rig.barrier()
+        clear_ms = z0.elapsed_time(z1) / reps
+        nbytes = width * height * 16
+        ar = max(out["allreduce"] - clear_ms, 1e-6)
+        reduce_info = {"bytes": nbytes, "reduce_to_root_ms": out["reduce_to_root"] - clear_ms, "allreduce_ms": ar,
+                       "frame_clear_ms": clear_ms,
+                       "allreduce_bus_gbs": 2 * (world - 1) / world * nbytes / (ar * 1e-3) / 1e9,
+                       "note": "hjk_reduce_frame on the render stream (the library's communicator, NCCL by dlopen); the "
+                               "frame clear that precedes each call is timed alone and subtracted; bus bandwidth = "
+                               "2(N-1)/N * S / t (nominal NVLink 5: 900 GB/s per direction)"}
+
+    info = {k: ctx.get_info(k) for k in ("bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "wave_paths",
+                                          "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_sms", "stack_overflows")}
+
+    ms, e2e_max = rig.max_over_ranks([ms, e2e_ms or 0.0])
+    rays, e2e_rays, ext_rays, sh_rays, launches = (int(v) for v in
+                                                   rig.sum_over_ranks([rays, e2e_rays, ext_rays, sh_rays, launches]))
+    peak, peak_src = measured_peaks()
+    wave_passes = max(1, min(sps, (info["wave_paths"] + width * height // 2) // (width * height)))
+    n_ext_launches = steps * (max_bounces + 1) * -(-sps // wave_passes)
+    ext_ms = kernel_ms.get("extend", 0.0)  # slot HJK_K_EXTEND times k_trace (extension + shadow rays) on this rank
+    trace_bytes = (EXTEND_BYTES_PER_RAY * ext_rays + SHADOW_BYTES_PER_RAY * sh_rays) / world
+    scene_bytes = SCENE_FETCH_BYTES_PER_RAY * rays / world if kind == "terrain" else 0.0
+    achieved = (trace_bytes + scene_bytes) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
+    pipe = (PIPE_BYTES_EXT * ext_rays + PIPE_BYTES_SHADOW * sh_rays + scene_bytes * world) / world / (ms * 1e-3) / 1e9
+    nm = ncu_metrics(kind)
+    rec = {
+        "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps,
+        "config": {"workload": label, "spp_per_step_per_gpu": sps, "blocks_per_step_per_gpu": sps * bpp,
+                   "parallelism": f"sample-pass dp{world}",
+                   "l2": "inputs larger than L2: the path state + queues of one wave (~200 B per path, GBs per wave) "
+                         "exceed the 126 MB L2",
+                   "image_mean": result_mean, "bvh": info,
+                   "scene_build_s": round(t_scene, 2), "bvh_build_upload_s": round(t_upload, 2)},
+        "rays": {"extension": ext_rays, "shadow": sh_rays, "per_path": rays / max(1, steps * sps * width * height * world)},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": {k: v / steps for k, v in kernel_ms.items()},
+        "roofline": {"kernel": "k_trace_coop", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": (nm["dram_bytes_per_ray"] * rays / world / n_ext_launches
+                                 if nm and nm.get("dram_bytes_per_ray") and n_ext_launches else None),
+                     "algorithmic_bytes_per_launch": (trace_bytes + scene_bytes) / n_ext_launches if n_ext_launches else None,
+                     "peak_source": peak_src,
+                     # what actually bounds traversal on a cache-resident scene (SURVEY 8d caveat): cycles with an
+                     # instruction issued / lanes per instruction, from the committed ncu summary (not measured live)
+                     "ncu": nm,
+                     "bytes_per_ray": {"extension": EXTEND_BYTES_PER_RAY, "shadow": SHADOW_BYTES_PER_RAY,
+                                       "scene_fetch": SCENE_FETCH_BYTES_PER_RAY if kind == "terrain" else 0},
+                     "launches": n_ext_launches,
+                     "avg_launch_ms": ext_ms / n_ext_launches if n_ext_launches else None,
+                     "share_of_step": ext_ms / ms if ms else None,
+                     "note": "traversal of a cache-resident BVH is issue/latency-bound, not HBM-bound "
+                             "(SURVEY.md §8d); see profiles/ for SM issue utilisation"},
+        "pipeline_bytes": {"achieved": pipe, "unit": "GB/s", "frac": pipe / peak},
+    }
+    if clocks is not None:
+        rec["clocks"] = clocks
+    if exact is not None:
+        rec["exact_ties"] = exact
+    if e2e_ms is not None:
+        rec["e2e"] = {"value": e2e_rays / (e2e_max * 1e-3) / 1e6, "unit": "Mrays/s",
+                      "h2d_bytes_per_step": int(slices[0].nbytes) * world, "d2h_bytes_per_step": width * height * 16,
+                      "ms_per_step": e2e_max / steps,
+                      "note": "bytes are whole-job per step: every rank uploads its block list, rank 0 alone reads the frame back"}
+    if reduce_info:
+        rec["reduce"] = reduce_info
+    return rec
+
+
+def run_strong(rig, wl, total_spp):
+    """A fixed job split over the ranks: `total_spp` sample passes of the workload, pass p -> rank p mod N, from the
+    scene upload (rank 0 builds the wide BVH and broadcasts it) to the normalised frame in rank 0's host memory.
+    Wall clock between two barriers, max over ranks — the one number here that is not device-timed, because the
+    BVH build is host work; the device time of the render calls is reported beside it."""
+    hj, torch = rig.hj, rig.torch
+    ctx, rank, world = rig.ctx, rig.rank, rig.world
+    label, kind, width, height, spp, max_bounces, _ = wl
+    gen = hj.ImageBlockGenerator(width, height, BLOCK, total_spp)
+    mine = hj.split_passes(gen.blocks(), gen.blocks_per_pass, rank, world)
+    compiled = make_scene(kind).compile(use_bvh=False)
+    out_host = torch.empty((height, width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    params = hj.make_params(max_bounces=max_bounces)
+    res = []
+    for attempt in range(2):  # the second run is reported (first: allocations, NCCL channel setup)
+        rig.barrier()
+        t0 = time.perf_counter()
+        ctx.scene_upload(compiled)
+        t1 = time.perf_counter()
+        ctx.frame_begin(width, height)
+        st = ctx.render(mine, params) if len(mine) else None
+        ctx.readback_root_ptr(0, out_host.data_ptr() if rank == 0 else 0, width * 16, normalise=True)
+        rig.barrier()
+        t2 = time.perf_counter()
+        res = [t2 - t0, t1 - t0, st.ms_total if st else 0.0, float(st.n_rays) if st else 0.0]
+    job_s, upload_s, render_ms = rig.max_over_ranks(res[:3])
+    rays = rig.sum_over_ranks([res[3]])[0]
+    return {"workload": f"{label.split(',')[0]} {width}x{height}, {total_spp} spp in total, max {max_bounces} bounces",
+            "scaling": "strong", "n_gpus": world, "job_s": job_s, "scene_upload_s": upload_s,
+            "render_device_ms": render_ms, "value": rays / job_s / 1e6, "unit": "Mrays/s",
+            "render_only_value": rays / (render_ms * 1e-3) / 1e6 if render_ms else None,
+            "note": "wall clock from hjk_scene_upload to the frame on rank 0's host (BVH build + broadcast, render, "
+                    "ncclReduce, readback), max over ranks"}
+
+
+def run_denoiser(rig, params):
+    """Reconstruction ("denoiser") bandwidth on 3840x2160 feature buffers (configs[4]), per GPU."""
+    hj = rig.hj
+    dw, dh = 3840, 2160
+    rng = np.random.default_rng(5 + rig.rank)
+    rad = np.exp(rng.standard_normal((dh, dw, 4), dtype=np.float32))
+    rad[..., 3] = 1.0
+    nrm = rng.standard_normal((dh, dw, 4), dtype=np.float32)
+    nrm[..., :3] /= np.linalg.norm(nrm[..., :3], axis=2, keepdims=True)
+    dblocks = hj.ImageBlockGenerator(dw, dh, BLOCK, 1).blocks()
+    dctx = hj.Context(rig.local_rank)
+    dctx.frame_begin(dw, dh)
+    dctx.denoise_upload(rad, nrm, dblocks)
+    dctx.denoise_resident(params, 5)
+    reps = 50
+    dms = dctx.denoise_resident(params, reps)
+    dctx.close()
+    dms = rig.max_over_ranks([dms])[0]
+    gbs = RECON_BYTES_PER_PX * dw * dh * reps / (dms * 1e-3) / 1e9
+    peak, _ = measured_peaks()
+    return {"workload": "3840x2160 synthetic feature buffers (random unit normals), 510 ImageBlocks/pass, R=2 "
+                        "(BASELINE.json configs[4]), per GPU (max time over ranks)",
+            "kernel": "k_recon", "ms_per_pass": dms / reps, "bytes_per_px": RECON_BYTES_PER_PX, "achieved": gbs,
+            "unit": "GB/s", "peak": peak, "frac": gbs / peak, "aggregate_gbs": gbs * rig.world}
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -262,11 +607,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-denoiser", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the terrain / spheres / spheres64 / strong objects")
     ap.add_argument("--cpu-seconds", type=float, default=100.0, help="wall budget of the --impl reference run")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    label, kind, width, height, spp, max_bounces, default_sps = wl
-    sps = args.spp_per_step or default_sps
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -276,235 +620,31 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
-    import torch
-    import torch.distributed as dist
-    import hijiki_b200 as hj
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    n_steps_total = args.warmup + args.steps
-    gen = hj.ImageBlockGenerator(width, height, BLOCK, spp)
-    bpp = gen.blocks_per_pass
-    # only the passes the run touches are generated (the list is a prefix of the job's list)
-    gen.num_samples = min(spp, n_steps_total * sps * world)
-    blocks = gen.blocks()
-    t0 = time.perf_counter()
-    compiled = make_scene(kind).compile(use_bvh=False)
-    t_scene = time.perf_counter() - t0
-    ctx = hj.Context(local_rank)
-    stream = torch.cuda.Stream(device=local_rank)
-    ctx.set_stream(stream.cuda_stream)
-    t0 = time.perf_counter()
-    ctx.scene_upload(compiled)
-    t_upload = time.perf_counter() - t0
-    ctx.frame_begin(width, height)
-    ctx.set_profiling(True)
-    params = hj.make_params(max_bounces=max_bounces)
-
-    # accumulator as a torch tensor (no copy) so torch.distributed can reduce it in place
-    acc_ptr, acc_n = ctx.accumulator_device_ptr()
-
-    class _Alias:
-        __cuda_array_interface__ = {"shape": (acc_n,), "typestr": "<f4", "data": (acc_ptr, False), "version": 2}
-
-    acc_t = torch.as_tensor(_Alias(), device=torch.device("cuda", local_rank))
-
-    def allreduce():
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_reduce(acc_t)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident arm: block lists uploaded before the timed region
-    slices = [step_slice(blocks, bpp, s, rank, world, sps) for s in range(n_steps_total)]
-    handles = [ctx.blocks_upload(s) for s in slices]
-    for s in range(args.warmup):
-        ctx.frame_begin(width, height)
-        ctx.render_resident(handles[s], 0, slices[s].size, params)
-        allreduce()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rays = ext_rays = sh_rays = launches = 0
-    kernel_ms = {}
-    ev0.record(stream)
-    for s in range(args.warmup, n_steps_total):
-        ctx.frame_begin(width, height)
-        st = ctx.render_resident(handles[s], 0, slices[s].size, params)
-        allreduce()
-        rays += st.n_rays
-        ext_rays += st.n_extension_rays
-        sh_rays += st.n_shadow_rays
-        launches += st.n_launches + (1 if world > 1 else 0)
-        for k, v in st.kernel_ms.items():
-            kernel_ms[k] = kernel_ms.get(k, 0.0) + v
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-
-    # exact-tie mode (HJK_RENDER_EXACT_TIES), two steps: what bit-identity with the reference on every ray costs
-    exact_params = hj.make_params(max_bounces=max_bounces, flags=hj.HJK_RENDER_EXACT_TIES)
-    exact_rays, exact_ms = 0, 0.0
-    for s in range(args.warmup, min(n_steps_total, args.warmup + 2)):
-        ctx.frame_begin(width, height)
-        st = ctx.render_resident(handles[s], 0, slices[s].size, exact_params)
-        exact_rays += st.n_rays
-        exact_ms += st.ms_total
-    exact_unresolved = ctx.get_info("unresolved_ties")
-    for h in handles:
-        ctx.blocks_free(h)
-
-    # ---------------- end-to-end arm: host block list in, normalised frame out, every step
-    e2e_ms, e2e_rays, result_mean = None, 0, None
-    if not args.no_e2e:
-        pinned_blocks = [torch.from_numpy(s.view(np.uint8).copy()).pin_memory() for s in slices]
-        out_host = torch.empty((height, width, 4), dtype=torch.float32).pin_memory()
-
-        def e2e_step(s):
-            ctx.frame_begin(width, height)
-            st = ctx.render((pinned_blocks[s].data_ptr(), slices[s].size), params)
-            allreduce()
-            ctx.readback_ptr(out_host.data_ptr(), width * 16, normalise=True)
-            return st.n_rays
-
-        for s in range(args.warmup):
-            e2e_step(s)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for s in range(args.warmup, n_steps_total):
-            e2e_rays += e2e_step(s)
-        e1.record(stream)
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        result_mean = float(out_host[..., :3].mean())
-
-    # the path's one collective, timed alone: all-reduce(sum) of the W x H float4 accumulator
-    allreduce_info = None
-    if world > 1:
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        allreduce()
-        a0.record(stream)
-        for _ in range(reps):
-            allreduce()
-        a1.record(stream)
-        barrier()
-        ar_ms = a0.elapsed_time(a1) / reps
-        nbytes = width * height * 16
-        allreduce_info = {"bytes": nbytes, "ms": ar_ms,
-                          "bus_gbs": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
-                          "note": "torch.distributed NCCL on the render stream; bus bandwidth = 2(N-1)/N * S / t "
-                                  "(nominal NVLink 5: 900 GB/s per direction)"}
-
-    info = {k: ctx.get_info(k) for k in ("bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "wave_paths",
-                                          "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_sms")}
-    ctx.close()
-
-    # ---------------- reconstruction ("denoiser") bandwidth on 3840x2160 feature buffers (configs[4])
-    denoiser = None
+    rig = Rig(rank, world, local_rank)
+    main_rec = run_workload(rig, wl, args.steps, args.warmup, args.spp_per_step, not args.no_e2e, True, True)
+    line = {"metric": "Mrays/s (all bounces)", "value": main_rec.pop("value"), "unit": main_rec.pop("unit"),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_rec.pop("ms_per_step"),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    main_rec.pop("steps"), main_rec.pop("warmup")
+    line.update(main_rec)
+    if not args.no_extras and args.workload == "cbox1080":
+        # the other BASELINE configs, measured the same way (device-resident + end to end), fewer steps
+        for name in ("terrain", "spheres", "spheres64"):
+            rec = run_workload(rig, WORKLOADS[name], min(args.steps, 3), 3, 0, not args.no_e2e, name != "spheres64", False)
+            rec["metric"] = "Mrays/s (all bounces)"
+            line[name] = rec
+        line["strong"] = run_strong(rig, wl, 256)
+    params = rig.hj.make_params(max_bounces=wl[5])
+    rig.ctx.close()
     if not args.no_denoiser:
-        dw, dh = 3840, 2160
-        rng = np.random.default_rng(5 + rank)
-        rad = np.exp(rng.standard_normal((dh, dw, 4), dtype=np.float32))
-        rad[..., 3] = 1.0
-        nrm = rng.standard_normal((dh, dw, 4), dtype=np.float32)
-        nrm[..., :3] /= np.linalg.norm(nrm[..., :3], axis=2, keepdims=True)
-        dblocks = hj.ImageBlockGenerator(dw, dh, BLOCK, 1).blocks()
-        dctx = hj.Context(local_rank)
-        dctx.frame_begin(dw, dh)
-        dctx.denoise_upload(rad, nrm, dblocks)
-        dctx.denoise_resident(params, 5)
-        reps = 50
-        dms = dctx.denoise_resident(params, reps)
-        gbs = RECON_BYTES_PER_PX * dw * dh * reps / (dms * 1e-3) / 1e9
-        denoiser = {"workload": "3840x2160 synthetic feature buffers (random unit normals), 510 ImageBlocks/pass, R=2 "
-                                "(BASELINE.json configs[4]), per GPU",
-                    "ms_per_pass": dms / reps, "bytes_per_px": RECON_BYTES_PER_PX, "achieved": gbs, "unit": "GB/s"}
-        dctx.close()
-
-    # ---------------- gather over ranks (max time, summed rays)
-    peak, peak_src = measured_peaks()
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), (float(t[1]) if e2e_ms is not None else None)
-        c = torch.tensor([rays, e2e_rays, ext_rays, sh_rays, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c)
-        rays, e2e_rays, ext_rays, sh_rays, launches = (int(v) for v in c.tolist())
+        line["denoiser"] = run_denoiser(rig, params)
     if rank == 0:
-        value = rays / (ms * 1e-3) / 1e6
-        wave_passes = max(1, min(sps, (info["wave_paths"] + width * height // 2) // (width * height)))
-        n_ext_launches = args.steps * (max_bounces + 1) * -(-sps // wave_passes)
-        ext_ms = kernel_ms.get("extend", 0.0)  # slot HJK_K_EXTEND times k_trace (extension + shadow rays)
-        trace_bytes = (EXTEND_BYTES_PER_RAY * ext_rays + SHADOW_BYTES_PER_RAY * sh_rays) / world
-        achieved = trace_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else None
-        pipe = (PIPE_BYTES_EXT * ext_rays + PIPE_BYTES_SHADOW * sh_rays) / world / (ms * 1e-3) / 1e9
-        line = {
-            "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "spp_per_step_per_gpu": sps, "blocks_per_step_per_gpu": sps * bpp,
-                       "parallelism": f"sample-pass dp{world}",
-                       "l2": "inputs larger than L2: the path state + queues of one wave (~200 B per path, GBs per wave) exceed the 126 MB L2",
-                       "image_mean": result_mean, "bvh": info,
-                       "scene_build_s": round(t_scene, 2), "bvh_build_upload_s": round(t_upload, 2)},
-            "rays": {"extension": ext_rays, "shadow": sh_rays,
-                     "per_path": rays / max(1, args.steps * sps * width * height * world)},
-            "gpu_launches": launches,
-            "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
-            "roofline": {"kernel": "k_trace_coop", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None,
-                         "traffic": (TRACE_DRAM_BYTES_PER_RAY_NCU * rays / world / n_ext_launches
-                                     if kind == "cbox" and n_ext_launches else None),
-                         "algorithmic_bytes_per_launch": trace_bytes / n_ext_launches if n_ext_launches else None,
-                         "traffic_source": "ncu DRAM bytes per traced ray (profiles/r01f, cbox) x rays per launch",
-                         "peak_source": peak_src,
-                         # what actually bounds traversal on a cache-resident scene (SURVEY 8d caveat): cycles with an
-                         # instruction issued / lanes per instruction, from the same ncu capture (not measured live)
-                         "issue_active_pct_ncu": 74.2 if kind == "cbox" else None,
-                         "lanes_per_instruction_ncu": 21.2 if kind == "cbox" else None,
-                         "bytes_per_ray": {"extension": EXTEND_BYTES_PER_RAY, "shadow": SHADOW_BYTES_PER_RAY},
-                         "launches": n_ext_launches,
-                         "avg_launch_ms": ext_ms / n_ext_launches if n_ext_launches else None,
-                         "share_of_step": ext_ms / ms if ms else None,
-                         "note": "traversal of a cache-resident BVH is issue/latency-bound, not HBM-bound "
-                                 "(SURVEY.md §8d); see profiles/ for SM issue utilisation"},
-            "pipeline_bytes": {"achieved": pipe, "unit": "GB/s", "frac": pipe / peak},
-            "clocks": clocks,
-            "exact_ties": {"value": exact_rays / (exact_ms * 1e-3) / 1e6 if exact_ms else None, "unit": "Mrays/s",
-                           "unresolved_clusters_last_step": exact_unresolved,
-                           "note": "this rank, 2 steps, HJK_RENDER_EXACT_TIES (the mode whose frames the parity tests "
-                                   "hold bit-identical to the oracle); unresolved = tie clusters longer than the "
-                                   "8*M_EPS window or 12 candidates, counted, each can move one sample"},
-        }
-        if e2e_ms is not None:
-            line["e2e"] = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
-                           "h2d_bytes_per_step": int(slices[0].nbytes), "d2h_bytes_per_step": width * height * 16,
-                           "ms_per_step": e2e_ms / args.steps}
-        if allreduce_info:
-            line["allreduce"] = allreduce_info
-        if denoiser:
-            denoiser["peak"] = peak
-            denoiser["frac"] = denoiser["achieved"] / peak
-            line["denoiser"] = denoiser
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(wl)
         emit(line)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        rig.dist.barrier()
+        rig.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -279,7 +279,12 @@ class Context:
         self._check(self.lib.hjk_read_features(self.ptr, root, as_ptr(out), out.strides[0]))
         return out
 
-    def reduce_frame(self, root: int = -1) -> float:
+    def reduce_frame(self, root: int = -1, timed: bool = True) -> float:
+        """Sum of the frame over the ranks (to every rank, or to ``root``).  ``timed`` waits for the collective and
+        returns its device time; otherwise the call only enqueues it."""
+        if not timed:
+            self._check(self.lib.hjk_reduce_frame(self.ptr, root, None))
+            return 0.0
         ms = C.c_float()
         self._check(self.lib.hjk_reduce_frame(self.ptr, root, C.byref(ms)))
         return ms.value

@@ -95,3 +95,20 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_never_maps_the_product_library():
+    import subprocess
+    """bench.py --impl reference builds its scene, BVH2 and block list with the tests-side host library and traces
+    with the oracle: libhijiki_b200.so must not be in the process at all."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-seconds', '1']\n"
+            "runpy.run_path('bench.py', run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "sys.stderr.write('MAPPED:' + ','.join(sorted({l.split()[-1] for l in maps.splitlines() if '.so' in l and "
+            "('hijiki' in l or 'oracle' in l or 'hosttest' in l)})))\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    mapped = r.stderr.split("MAPPED:")[-1]
+    assert "liboracle.so" in mapped and "libhjk_hosttest.so" in mapped
+    assert "libhijiki_b200" not in mapped, mapped
