@@ -116,6 +116,9 @@ struct HjkContext {
   int coop_trace = 1;    // 1 = k_trace_coop: pooled primitive tests (default mode only); 0 = per-lane k_trace
   uint32_t coop_batch_cost = 180;
   int blocks_coop[3] = {0, 0, 0};  // k_trace_coop<GUARD = 0, 1, 2>
+  int blocks_batch = 0;            // k_trace_batch (hjk_trace_first_hit)
+  uint32_t stack_cap_coop = 8, stack_cap_lane = 16;  // traversal-stack entries per thread (see trace_launch_shape)
+  bool lane_postpones = true;
   int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU LBVH builder
   int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
   int bvh_broadcast = 1;  // several ranks: rank 0 builds the wide BVH, the others receive it over ncclBroadcast
@@ -438,11 +441,14 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   w.fetch_threshold = c->fetch_threshold;
   // a postponed primitive group takes a second stack entry on its level: only trees of at most kMaxStack / 2 levels
   // (8^16 leaves) leave room for that, deeper ones are walked without postponing
-  w.postpone_lanes = 2 * c->bvh_host_stats.depth <= (uint32_t)kMaxStack ? c->postpone_lanes : 0u;
+  w.postpone_lanes = c->lane_postpones ? c->postpone_lanes : 0u;
   w.unresolved = c->d_unresolved.p;
   w.coop_batch_cost = c->coop_batch_cost;
   const bool exact = (prm->flags & HJK_RENDER_EXACT_TIES) != 0;
   const bool guard = c->scene.num_spheres != 0;
+  const bool use_coop = c->coop_trace && !exact;
+  w.stack_cap = use_coop ? c->stack_cap_coop : c->stack_cap_lane;
+  const size_t sm_trav = (size_t)w.stack_cap * kTravThreads * sizeof(uint2);
   const int g_trav = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_trav_v[guard][exact]);
   const int g_tile = grid_for(c, c->blocks_tile);
   const int g_light = grid_for(c, c->blocks_light);
@@ -469,23 +475,23 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
     for (uint32_t b = 0;; b++) {
       {
         KernelTimer t(c, stats, HJK_K_EXTEND);
-        if (c->coop_trace && !exact) {
+        if (use_coop) {
           const int gv = guard ? (c->bvh_all_guarded ? 2 : 1) : 0;
           const int g_coop = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_coop[gv]);
           if (gv == 2)
-            k_trace_coop<2><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+            k_trace_coop<2><<<g_coop, kTravThreads, sm_trav, c->stream>>>(w, b, last);
           else if (gv == 1)
-            k_trace_coop<1><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+            k_trace_coop<1><<<g_coop, kTravThreads, sm_trav, c->stream>>>(w, b, last);
           else
-            k_trace_coop<0><<<g_coop, kTravThreads, 0, c->stream>>>(w, b, last);
+            k_trace_coop<0><<<g_coop, kTravThreads, sm_trav, c->stream>>>(w, b, last);
         } else if (guard && exact)
-          k_trace<true, true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+          k_trace<true, true><<<g_trav, kTravThreads, sm_trav, c->stream>>>(w, b, last);
         else if (guard)
-          k_trace<true, false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+          k_trace<true, false><<<g_trav, kTravThreads, sm_trav, c->stream>>>(w, b, last);
         else if (exact)
-          k_trace<false, true><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+          k_trace<false, true><<<g_trav, kTravThreads, sm_trav, c->stream>>>(w, b, last);
         else
-          k_trace<false, false><<<g_trav, kTravThreads, 0, c->stream>>>(w, b, last);
+          k_trace<false, false><<<g_trav, kTravThreads, sm_trav, c->stream>>>(w, b, last);
         launches++;
       }
       if (b == last) break;
@@ -654,6 +660,37 @@ const char* hjk_version(void) { return "hijiki_b200 0.1 (sm_100a)"; }
 
 const char* hjk_last_error(const HjkContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
+// Launch shape of the trace kernels for a tree of `depth` levels: the traversal stack is dynamic shared memory, one
+// entry per level (+1) in k_trace_coop, two per level where the per-lane kernels postpone primitive groups (only
+// when that still fits kMaxStack entries), and the resident CTAs per SM follow from it.
+static void trace_launch_shape(HjkContext* c, uint32_t depth) {
+  c->stack_cap_coop = std::max<uint32_t>(depth + 1, 2);
+  c->lane_postpones = 2 * depth + 2 <= (uint32_t)kMaxStack;
+  c->stack_cap_lane = c->lane_postpones ? 2 * depth + 2 : std::max<uint32_t>(depth + 1, 2);
+  const size_t sm_coop = (size_t)c->stack_cap_coop * kTravThreads * sizeof(uint2);
+  const size_t sm_lane = (size_t)c->stack_cap_lane * kTravThreads * sizeof(uint2);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, false>, kTravThreads, sm_lane);
+  c->blocks_trav_v[0][0] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true>, kTravThreads, sm_lane);
+  c->blocks_trav_v[0][1] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false>, kTravThreads, sm_lane);
+  c->blocks_trav_v[1][0] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, kTravThreads, sm_lane);
+  c->blocks_trav_v[1][1] = std::max(occ, 1);
+  c->blocks_trav = c->blocks_trav_v[0][0];
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, false>, kTravThreads, sm_lane);
+  c->blocks_batch = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<1, true>, kTravThreads, sm_lane);
+  c->blocks_batch = std::max(std::min(c->blocks_batch, occ), 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<0>, kTravThreads, sm_coop);
+  c->blocks_coop[0] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<1>, kTravThreads, sm_coop);
+  c->blocks_coop[1] = std::max(occ, 1);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<2>, kTravThreads, sm_coop);
+  c->blocks_coop[2] = std::max(occ, 1);
+}
+
 static int create_one(int device, HjkContext** out_ctx) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -686,22 +723,8 @@ static int create_one(int device, HjkContext** out_ctx) {
   c->own_stream = true;
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  trace_launch_shape(c, 7);  // refreshed by every scene upload for the depth of its tree
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, false>, kTravThreads, 0);
-  c->blocks_trav_v[0][0] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<false, true>, kTravThreads, 0);
-  c->blocks_trav_v[0][1] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, false>, kTravThreads, 0);
-  c->blocks_trav_v[1][0] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<true, true>, kTravThreads, 0);
-  c->blocks_trav_v[1][1] = std::max(occ, 1);
-  c->blocks_trav = c->blocks_trav_v[0][0];
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<0>, kTravThreads, 0);
-  c->blocks_coop[0] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<1>, kTravThreads, 0);
-  c->blocks_coop[1] = std::max(occ, 1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_coop<2>, kTravThreads, 0);
-  c->blocks_coop[2] = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kShadeThreads, 0);
   c->blocks_tile = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
@@ -955,6 +978,7 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   bvh.prims.clear();
   bvh.prims.shrink_to_fit();
   c->bvh_host_stats = bvh;
+  trace_launch_shape(c, bvh.depth);
   {
     const unsigned int zero = 0;
     HJK_CUDA(c, cudaMemcpyToSymbol(g_stack_overflows, &zero, sizeof zero));
@@ -1284,14 +1308,15 @@ int hjk_trace_first_hit_eps(HjkContext* c, const HjkRay* rays, uint64_t n_rays, 
   HJK_CUDA(c, cudaMemcpyAsync(d_o.p, ho.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
   HJK_CUDA(c, cudaMemcpyAsync(d_d.p, hd.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
   HJK_CUDA(c, cudaMemsetAsync(d_cur.p, 0, 8, c->stream));
-  const int g = grid_for(c, c->blocks_trav);
+  const int g = grid_for(c, c->blocks_batch);
   const bool guard = c->scene.num_spheres != 0;
   const uint32_t flavour = (any_hit & 1) ? kAnyHitBit : 0u;
   const bool exact = (any_hit & 2) != 0;
-  const int postpone = 2 * c->bvh_host_stats.depth <= (uint32_t)kMaxStack ? kPostponeLanes : 0;  // see render_blocks
+  const int postpone = c->lane_postpones ? kPostponeLanes : 0;
+  const size_t sm_trav = (size_t)c->stack_cap_lane * kTravThreads * sizeof(uint2);
 #define HJK_BATCH(G, E) \
-  k_trace_batch<G, E><<<g, kTravThreads, 0, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, flavour, \
-                                                         postpone)
+  k_trace_batch<G, E><<<g, kTravThreads, sm_trav, c->stream>>>(c->scene, d_o.p, d_d.p, d_h.p, (uint32_t)n, d_cur.p, eps, \
+                                                               flavour, postpone, (int)c->stack_cap_lane)
   if (guard && exact)
     HJK_BATCH(true, true);
   else if (guard)

@@ -5,7 +5,7 @@
 //   k_raygen      one thread per path slot: RNG seed, camera ray, layer initialisation
 //   k_trace_coop  persistent warps pull the extension rays of bounce b (closest hit = "extend") and
 //                 the shadow rays of bounce b-1 (any hit) from one work range and walk the 8-wide
-//                 BVH, short stack in shared memory; the primitive tests of a warp are pooled over
+//                 BVH, stack in shared memory (sized to the tree's depth at launch); the primitive tests of a warp are pooled over
 //                 its 32 lanes when the per-lane counts are skewed (the default trace kernel)
 //   k_trace       the same with a per-lane primitive loop: exact-tie mode, hjk_trace_first_hit
 //   k_shade       per tile of the queue: misses dropped, hits counting-sorted by material tag in
@@ -70,11 +70,16 @@ struct WaveDev {
   uint32_t fetch_threshold;      // refill a warp when fewer lanes than this are busy
   uint32_t postpone_lanes;       // postpone primitive tests that fewer lanes than this would run
   uint32_t coop_batch_cost;      // pooled primitive tests: assumed instructions per batch of 32 (0 = always pool)
+  uint32_t stack_cap;            // entries per thread of the launch's shared-memory traversal stack
   uint32_t* unresolved;          // exact-tie mode: rays whose tie cluster outgrew the window/list
 };
 
 #ifndef HJK_TRACE_COOP_MIN_BLOCKS
-#define HJK_TRACE_COOP_MIN_BLOCKS 9  // measured 7/8/9/10: 33.9 / 32.8 / 32.4 / 39.1 ms per step on cbox
+// 8 CTAs = 64 registers: no spills and (the stack being shared memory) no local memory at all.  At 9 CTAs = 56
+// registers the kernel spills 36-52 bytes, and whether that costs nothing or 33 % of the kernel (32.1 vs 42.8 ms per
+// step on cbox: local-memory sectors missing L1, long-scoreboard stalls x5) flipped with unrelated one-line changes
+// elsewhere in the file (profiles/README.md r02d).  Measured 8 / 9: 32.07 / 32.19-42.75 ms.
+#define HJK_TRACE_COOP_MIN_BLOCKS 8
 #endif
 #ifndef HJK_TRACE_MIN_BLOCKS
 #define HJK_TRACE_MIN_BLOCKS 9 /* 56 registers, no spills: 36 warps per SM (measured best of 8/9/10/12) */
@@ -83,12 +88,10 @@ struct WaveDev {
 #define HJK_TRAV_THREADS 128
 #endif
 constexpr int kTravThreads = HJK_TRAV_THREADS;
-#ifndef HJK_SM_STACK
-#define HJK_SM_STACK 8
-#endif
-constexpr int kSmStack = HJK_SM_STACK;  // stack entries kept in shared memory per thread
-constexpr int kLocalStack = 32 - HJK_SM_STACK;  // overflow entries in local memory
-constexpr int kMaxStack = kSmStack + kLocalStack;
+// The traversal stack lives entirely in shared memory, sized at launch to the tree at hand (dynamic shared memory:
+// stack_cap entries of 8 bytes per thread, thread-interleaved): one node-group entry per level, plus one postponed
+// primitive group per level in the per-lane kernel.  kMaxStack bounds the tree depth hjk_scene_upload accepts.
+constexpr int kMaxStack = 32;
 constexpr int kFetchThreshold = 20;  // refill a warp when fewer lanes than this are busy
 constexpr int kPostponeLanes = 8;    // postpone primitive tests that fewer lanes than this would run
 #ifndef HJK_TILE_THREADS
@@ -184,34 +187,28 @@ __global__ void __launch_bounds__(kTileThreads) k_raygen(WaveDev w) {
 }
 
 // ---------------------------------------------------------------- traversal
-// Set when a traversal-stack entry did not fit (a lost entry can lose a hit): hjk_scene_upload refuses trees that
-// could get here, so this stays 0.  A module-level flag written by one predicated store: no pointer to carry
-// through the traversal loop (its register budget is spent: a pointer in DevStack cost 30 % of the trace kernel)
-// and no divergent region in push() (an atomicAdd there cost the exact-tie kernel 27 %).  Read by
-// hjk_get_info("stack_overflows").
+// Set when a traversal-stack entry did not fit (a lost entry can lose a hit): the launch sizes the stack to the tree
+// (depth + 1 entries, twice that where primitive groups are postponed), so this stays 0.  A module-level flag
+// written by one predicated store; read by hjk_get_info("stack_overflows").
 __device__ unsigned int g_stack_overflows;
 struct DevStack {
-  uint2* sm;  // this thread's column of the shared-memory stack (stride kTravThreads)
-  uint2 local[kLocalStack];
-  int n;
-  __device__ __forceinline__ int size() const { return n; }
+  uint2* sm;  // this thread's column of the CTA's shared-memory stack (stride kTravThreads)
+  int n, cap;
   __device__ __forceinline__ void push(uint32_t a, uint32_t b) {
-    if (n < kSmStack) {
+    if (n < cap)
       sm[n * kTravThreads] = make_uint2(a, b);
-    } else if (n < kMaxStack) {
-      local[n - kSmStack] = make_uint2(a, b);
-    } else {
+    else
       g_stack_overflows = 1u;
-    }
     n++;
   }
   __device__ __forceinline__ void pop(uint32_t& a, uint32_t& b) {
     n--;
-    const uint2 v = n < kSmStack ? sm[n * kTravThreads] : local[(n < kMaxStack ? n : kMaxStack - 1) - kSmStack];
+    const uint2 v = sm[(n < cap ? n : cap - 1) * kTravThreads];
     a = v.x, b = v.y;
   }
   __device__ __forceinline__ bool empty() const { return n == 0; }
 };
+extern __shared__ __align__(16) uint2 dyn_trav_stack[];  // [stack_cap][kTravThreads]
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -280,12 +277,12 @@ struct WarpPolicy {
 template <int GUARD, bool EXACT, class IO>
 __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io, uint32_t n,
                                                uint32_t* cursor, float eps, int fetch_threshold,
-                                               int postpone_lanes, uint32_t* unresolved) {
-  __shared__ uint2 sm_stack[kSmStack * kTravThreads];
+                                               int postpone_lanes, uint32_t* unresolved, int stack_cap) {
   const uint32_t lane = threadIdx.x & 31u;
   DevStack st;
-  st.sm = sm_stack + threadIdx.x;
+  st.sm = dyn_trav_stack + threadIdx.x;
   st.n = 0;
+  st.cap = stack_cap;
   TravState s;
   typename std::conditional<EXACT, TieCands, NoCands>::type cands;
   cands.reset();
@@ -334,14 +331,15 @@ __device__ __forceinline__ void traverse_queue(const SceneDev& sc, const IO& io,
 // The exact-tie mode keeps the per-lane loop (it must record every candidate).
 template <int GUARD, class IO>
 __device__ __forceinline__ void traverse_queue_coop(const SceneDev& sc, const IO& io, uint32_t n, uint32_t* cursor,
-                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost) {
-  __shared__ uint2 sm_stack[kSmStack * kTravThreads];
+                                                    float eps, int fetch_threshold, uint32_t coop_batch_cost,
+                                                    int stack_cap) {
   __shared__ unsigned long long sm_best[kTravThreads];
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t FULL = 0xFFFFFFFFu;
   DevStack st;
-  st.sm = sm_stack + threadIdx.x;
+  st.sm = dyn_trav_stack + threadIdx.x;
   st.n = 0;
+  st.cap = stack_cap;
   TravState s;
   s.tg_y = 0, s.ng_y = 0;
   bool active = false, exhausted = false;
@@ -509,7 +507,7 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_MIN_BLOCKS
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
   const WaveIO io{w, w.ray_o[bounce & 1u], w.ray_d[bounce & 1u], n_shadow};
   traverse_queue<GUARD, EXACT>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
-                               (int)w.postpone_lanes, w.unresolved);
+                               (int)w.postpone_lanes, w.unresolved, (int)w.stack_cap);
 }
 // same work, pooled primitive tests (traverse_queue_coop)
 template <int GUARD>
@@ -519,15 +517,15 @@ __global__ void __launch_bounds__(kTravThreads, GUARD ? 8 : HJK_TRACE_COOP_MIN_B
   const uint32_t n_shadow = bounce > 0 ? w.counters[(size_t)(bounce - 1) * CTR_STRIDE + CTR_SHADOW] : 0u;
   const WaveIO io{w, w.ray_o[bounce & 1u], w.ray_d[bounce & 1u], n_shadow};
   traverse_queue_coop<GUARD>(w.scene, io, n_shadow + n_ext, ctr + CTR_EXT_CURSOR, w.eps, (int)w.fetch_threshold,
-                             w.coop_batch_cost);
+                             w.coop_batch_cost, (int)w.stack_cap);
 }
 // cursor[0] = work cursor, cursor[1] = unresolved-tie counter (exact mode)
 template <int GUARD, bool EXACT>
 __global__ void __launch_bounds__(kTravThreads) k_trace_batch(SceneDev sc, const f4* ray_o, const f4* ray_d,
                                                               f4* hit, uint32_t n, uint32_t* cursor, float eps,
-                                                              uint32_t flavour, int postpone_lanes) {
+                                                              uint32_t flavour, int postpone_lanes, int stack_cap) {
   const BatchIO io{sc, ray_o, ray_d, hit, flavour};
-  traverse_queue<GUARD, EXACT>(sc, io, n, cursor, eps, kFetchThreshold, postpone_lanes, cursor + 1);
+  traverse_queue<GUARD, EXACT>(sc, io, n, cursor, eps, kFetchThreshold, postpone_lanes, cursor + 1, stack_cap);
 }
 
 // ---------------------------------------------------------------- sort + shade
