@@ -691,6 +691,7 @@ static void trace_launch_shape(HjkContext* c, uint32_t depth) {
   c->blocks_coop[2] = std::max(occ, 1);
 }
 
+static void destroy_one(HjkContext* c);
 static int create_one(int device, HjkContext** out_ctx) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -730,6 +731,22 @@ static int create_one(int device, HjkContext** out_ctx) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
   c->blocks_light = std::max(occ, 1);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail("kernel image (built for sm_100a)", e);
+  // tuning sweeps without touching the host program: HJK_OPTIONS="key=value,key=value" (hjk_set_option keys)
+  if (const char* env = getenv("HJK_OPTIONS")) {
+    std::string all(env);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      const size_t end = std::min(all.find(',', pos), all.size());
+      const std::string kv = all.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos && hjk_set_option(c, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1)) != HJK_OK) {
+        g_create_error = "HJK_OPTIONS: " + c->error;
+        destroy_one(c);
+        return HJK_ERR_INVALID_ARGUMENT;
+      }
+      pos = end + 1;
+    }
+  }
   *out_ctx = c;
   return HJK_OK;
 }
@@ -877,7 +894,7 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   std::string err;
   bool built_on_gpu = false;
   c->bvh_build_ms = 0.f;
-  const bool bcast = c->comm && c->n_ranks > 1 && c->members.size() <= 1 && c->bvh_broadcast;
+  const bool bcast = c->comm && c->n_ranks > 1 && c->members.size() <= 1 && !c->group_parent && c->bvh_broadcast;
   auto all_guarded = [](const WideBvh& b) {
     if (b.nodes.empty()) return false;
     for (const WideNode& wn : b.nodes)

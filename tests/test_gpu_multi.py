@@ -29,6 +29,18 @@ def _n_gpus():
 
 
 def _worker(rank, world, conn, out_path, spp):
+    import faulthandler
+    import traceback
+    faulthandler.dump_traceback_later(120, exit=True)  # a hung collective must not outlive the test
+    try:
+        _worker_body(rank, world, conn, out_path, spp)
+    except BaseException:
+        with open(out_path + ".err", "w") as f:
+            f.write(traceback.format_exc())
+        raise
+
+
+def _worker_body(rank, world, conn, out_path, spp):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     import hijiki_b200 as hj
@@ -81,12 +93,19 @@ def test_library_communicator_reduce(tmp_path, spp):
     ctx = mp.get_context("spawn")
     a, b = ctx.Pipe()
     outs = [str(tmp_path / f"acc{r}.npy") for r in range(2)]
-    procs = [ctx.Process(target=_worker, args=(r, 2, a if r == 0 else b, outs[r], spp)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, a if r == 0 else b, outs[r], spp), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=300)
-        assert p.exitcode == 0
+    try:
+        for p in procs:
+            p.join(timeout=200)
+        errors = [open(o + ".err").read() for o in outs if os.path.exists(o + ".err")]
+        assert not errors, "\n".join(errors)
+        assert [p.exitcode for p in procs] == [0, 0]
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     acc0, acc1 = np.load(outs[0]), np.load(outs[1])
     assert np.array_equal(acc0, acc1)  # both ranks hold the reduced frame
     full, feat = _single(spp, features=True)
