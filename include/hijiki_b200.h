@@ -311,8 +311,9 @@ HJK_API int hjk_denoise_resident(HjkContext* ctx, const HjkParams* params, uint3
  *   - hjk_readback / hjk_readback_root / hjk_read_features sum the frame over the ranks, once per frame. */
 HJK_API int hjk_comm_unique_id(void* out_id128);
 HJK_API int hjk_comm_init(HjkContext* ctx, const void* id128, int rank, int n_ranks);
-/* The frame's reduction on its own (what the readbacks do first; a no-op when the frame has not changed since
- * the last one).  root < 0: ncclAllReduce, else ncclReduce to `root`.  out_ms optional (device time). */
+/* The frame's reduction on its own (what the readbacks do first).  A collective: every rank calls it, with the
+ * same root, the same number of times.  root < 0: ncclAllReduce, else ncclReduce to `root`.  out_ms optional
+ * (device time). */
 HJK_API int hjk_reduce_frame(HjkContext* ctx, int root, float* out_ms);
 HJK_API int hjk_allreduce_accumulator(HjkContext* ctx, float* out_ms); /* = hjk_reduce_frame(ctx, -1, out_ms) */
 
