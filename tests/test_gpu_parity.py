@@ -620,3 +620,64 @@ def test_feature_buffers_average_the_first_hit_features(gpu_ctx):
     assert np.array_equal(acc.view(np.uint32), gpu_ctx.readback(normalise=False).view(np.uint32))
     with pytest.raises(hj.HijikiError):
         gpu_ctx.read_features()  # option off
+
+
+def _chain_scene(n=700, ratio=1.12):
+    """Triangles shrinking geometrically towards the origin: the SAH builder peels them off scale by scale and the
+    wide BVH comes out 15 levels deep — twice the depth of any BASELINE scene, deeper than the eight stack entries the
+    trace kernels used to keep in shared memory."""
+    verts, tris, mats = [], [], []
+    for k in range(n):
+        s = ratio ** (-k)
+        z = 0.2 * s  # no two in one plane, no two overlapping: hits of different triangles differ in t
+        verts += [(s, 0, z, 0, 0, 0, 1, 0), (1.1 * s, 0, z, 1, 0, 0, 1, 0), (s, 0.3 * s, z, 0, 0, 0, 1, 1)]
+        tris.append((3 * k, 3 * k + 1, 3 * k + 2))
+        mats.append((_abi.MAT_EMISSIVE if k % 50 == 0 else _abi.MAT_DIFFUSE, 0))
+    return _libs.CustomScene(((0.4, 0.1, 2.5), (0.0, 0.0, 0.0, 1.0), 35.0), triangles=tris, vertices=verts,
+                             materials=mats, diffuse=[(0.6, 0.6, 0.6, 0)], emissive=[(5, 5, 5, 0)])
+
+
+def test_deep_tree_traversal_stack(gpu_ctx):
+    """A 15-level wide BVH: the launch sizes the shared-memory traversal stack to the tree (16 entries for the pooled
+    kernel, 32 where primitive groups are postponed); hits stay exact and no stack entry is ever dropped."""
+    scene = _chain_scene()
+    gpu_ctx.scene_upload(scene)
+    depth = gpu_ctx.get_info("bvh_depth")
+    assert depth >= 14, depth
+    rng = np.random.default_rng(12)
+    n = 30000
+    k = rng.integers(0, 160, n)  # down to triangles of 1e-8: the deepest levels of the tree
+    s = 1.12 ** (-k.astype(np.float64))
+    target = np.stack([s * (1.0 + 0.1 * rng.random(n)), 0.3 * s * rng.random(n), 0.2 * s], axis=1)
+    origin = np.stack([rng.uniform(-0.2, 1.5, n), rng.uniform(-0.3, 0.6, n), rng.uniform(0.5, 2.0, n)], axis=1)
+    d = target - origin
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros(n, dtype=_abi.RAY_DTYPE)
+    rays["origin"], rays["direction"] = origin.astype(np.float32), d.astype(np.float32)
+    rays["t_min"], rays["t_max"] = 1e-4, np.inf
+    eps = 1e-9  # M_EPS as a parameter: at 1e-4 every triangle below that size would be one tie cluster
+    O = _libs.oracle()
+    ids_o, t_o, uv_o, tie = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
+    assert O.orc_trace(C.byref(scene.view), _libs.ptr(rays), n, 2, eps, _libs.ptr(ids_o), _libs.ptr(t_o), _libs.ptr(uv_o),
+                       _libs.ptr(tie), 0) == 0
+    ids_g, t_g, uv_g = gpu_ctx.trace_first_hit(rays, eps=eps)
+    keep = (tie == 0) & np.isfinite(t_o)
+    assert (ids_o >= 0).mean() > 0.2 and keep.mean() > 0.85
+    ids_e, _, _ = gpu_ctx.trace_first_hit(rays, exact_ties=True, eps=eps)
+    assert (ids_e != ids_o).sum() <= gpu_ctx.get_info("unresolved_ties")
+    assert np.array_equal(ids_o[keep], ids_g[keep])
+    hit = keep & (ids_o >= 0)
+    assert np.array_equal(t_o[hit].view(np.uint32), t_g[hit].view(np.uint32))
+    # whole frames through both trace kernels (default = pooled k_trace_coop, exact-tie = per-lane k_trace)
+    w, h, bs = 96, 64, 64
+    blocks = hj.ImageBlockGenerator(w, h, bs, 2).blocks()
+    acc_o, ost = _oracle_render(scene, blocks, 8, bs, 2)
+    for flags in (0, hj.HJK_RENDER_EXACT_TIES):
+        gpu_ctx.frame_begin(w, h)
+        st = gpu_ctx.render(blocks, hj.make_params(max_bounces=8, flags=flags))
+        acc_g = gpu_ctx.readback(normalise=False)
+        diff = (acc_o.view(np.uint32) != acc_g.view(np.uint32)).any(axis=2)
+        budget = 25 * (4 if flags == 0 else gpu_ctx.get_info("unresolved_ties"))
+        assert diff.sum() <= budget, (flags, int(diff.sum()))
+    assert gpu_ctx.get_info("stack_overflows") == 0
+    print(f"chain scene: wide BVH depth {depth}, {int((ids_o >= 0).sum())} of {n} probe rays hit, {int(tie.sum())} ties")

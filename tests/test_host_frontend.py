@@ -140,6 +140,48 @@ def _build_c_example(tmp_path):
     return exe
 
 
+def _build_c_example_static(tmp_path):
+    """The link a Rust host gets: libhijiki_b200.a + exactly the libraries bindings/rust/build.rs prints as
+    cargo:rustc-link-lib / rustc-link-search (parsed from build.rs, so the two cannot drift apart)."""
+    import re
+    import subprocess
+    src = open(os.path.join(_libs.ROOT, "bindings", "rust", "build.rs")).read()
+    search = re.findall(r'rustc-link-search=native=([^"{}]+)"', src)      # literal paths (the OUT_DIR one is ours)
+    static = re.findall(r'rustc-link-lib=static=(\w+)', src)
+    dynamic = re.search(r'for l in \[([^\]]+)\]', src).group(1).replace('"', "").replace(" ", "").split(",")
+    assert static[0] == "hijiki_b200" and "cudart_static" in static and "stdc++" in dynamic
+    exe = str(tmp_path / "render_c_static")
+    lib_dir = os.path.dirname(_abi.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-I", os.path.join(_libs.ROOT, "include"), os.path.join(_libs.ROOT, "examples", "render_c.c"),
+           "-L", lib_dir] + [f"-L{p}" for p in search] + [f"-l:lib{n}.a" for n in static] + [f"-l{n}" for n in dynamic] + \
+          ["-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "hijiki" not in ldd and "cudart" not in ldd  # both are inside the executable
+    return exe
+
+
+def test_c_host_links_the_static_library_with_the_rust_link_line(tmp_path):
+    import subprocess
+    exe = _build_c_example_static(tmp_path)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is covered by the gpu-marked test")
+    r = subprocess.run([exe, _libs.CBOX_OBJ, "64", "48", "1", str(tmp_path / "o.exr")], capture_output=True, text=True)
+    assert r.returncode == 1 and "hjk_create" in r.stderr
+
+
+@pytest.mark.gpu
+def test_statically_linked_c_host_renders(tmp_path):
+    import subprocess
+    exe = _build_c_example_static(tmp_path)
+    out = tmp_path / "o.exr"
+    r = subprocess.run([exe, _libs.CBOX_OBJ, "128", "96", "2", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Integrated 24576 paths" in r.stdout and out.stat().st_size > 128 * 96 * 12
+
+
 def test_c_host_compiles_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
     """include/hijiki_b200.h is plain C99 (-pedantic -Werror) and examples/render_c.c — the reference's main()
     over the C ABI — links against the library; without a CUDA device it stops at hjk_create with a message."""
