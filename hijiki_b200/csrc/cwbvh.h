@@ -10,7 +10,7 @@ namespace hjk {
 
 // 80-byte node = five 16-byte loads:
 //   q0: origin.xyz, {ex, ey, ez, imask}
-//   q1: child_base, prim_base | kWideHasSpheres, meta[0..3], meta[4..7]
+//   q1: child_base, prim_base | kWideHasSpheres | kWideOnlySpheres, meta[0..3], meta[4..7]
 //   q2: qlo_x[0..7], qlo_y[0..7]      q3: qlo_z[0..7], qhi_x[0..7]      q4: qhi_y[0..7], qhi_z[0..7]
 // Child box i on axis a spans origin[a] + q{lo,hi}_a[i] * 2^(e[a]-127).
 // meta[i]: 0 = empty slot; inner child = 0b001'11sss (sss = slot, bit index 24+slot);
@@ -52,6 +52,9 @@ enum : uint32_t { kWideMaxLeafPrims = 3, kWideMaxNodePrims = 24 };
 // Top bit of WideNode::prim_base: a sphere lives somewhere below this node (in one of its leaf children or in
 // a descendant).  Only such nodes need the traversal's sphere guard (traverse.cuh): triangle and quad tests
 // are geometric for any direction length, so the rest of the tree is culled with the plain slab test.
-enum : uint32_t { kWideHasSpheres = 0x80000000u, kWidePrimBaseMask = 0x7FFFFFFFu };
+// Second bit: EVERY primitive below the node is a sphere.  For directions shorter than unit length the reference's
+// sphere test can only accept spheres close to the ray origin (traverse.cuh, "far clip"), so such subtrees are
+// walked with a finite far distance.
+enum : uint32_t { kWideHasSpheres = 0x80000000u, kWideOnlySpheres = 0x40000000u, kWidePrimBaseMask = 0x3FFFFFFFu };
 
 }  // namespace hjk

@@ -365,7 +365,8 @@ __global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const
     }
     wn.imask = 0;
     wn.child_base = child_base;
-    wn.prim_base = prim_base | (s.S ? kWideHasSpheres : 0u);  // no per-subtree knowledge here: all or none
+    // no per-subtree knowledge here: all or none
+    wn.prim_base = prim_base | (s.S ? kWideHasSpheres : 0u) | (s.S && !s.Q && !s.T ? kWideOnlySpheres : 0u);
     uint32_t inner_rank = 0, prim_off = 0;
     for (int sl = 0; sl < 8; sl++) {
       const int c = child_in_slot[sl];

@@ -63,6 +63,7 @@ struct TravState {
   // sphere guard (see trav_init): per-ray constants of the per-node box inflation, box-test interval
   float guard_e, guard_lo;
   float box_tmin, box_tmax_scale;
+  float sph_clip;  // far clip of sphere-only subtrees (directions shorter than unit length), else +inf
   // exact-tie mode (see TieCands): boxes are culled against t_cull, tmax stays the ray's own
   float t_cull;
 };
@@ -85,6 +86,13 @@ HJK_HD float safe_rcp(float d) {
 //     s^2 >= 1:  Delta = sqrt(r_min^2 + L^2 (1 - 1/s^2)) - r_min      s^2 < 1:  Delta = r_max (1/s - 1)
 // For |s^2 - 1| of a few ulps this degenerates to a pad of ~1e-7 L^2 / r; for scenes without spheres
 // it is compiled out (triangle and quad tests are homogeneous in d, hence geometric for any s).
+// FAR CLIP.  For s^2 < 1 the discriminant of the reference's quadratic, 4 (d.l)^2 - 4 (L^2 - r^2), is negative
+// whenever L^2 (1 - s^2) > r^2 (because (d.l)^2 <= s^2 L^2): a sphere farther than r / sqrt(1 - s^2) from the ray
+// ORIGIN is never accepted, however the ray points.  For the others both roots obey |t| <= |b| + r <= 2 s L + r, so
+// every accepted sphere hit has t <= (2 s / sqrt(1 - s^2) + 1) r_max.  Subtrees that hold nothing but spheres
+// (kWideOnlySpheres) are therefore walked with that far distance — along specular chains the directions the
+// reference arithmetic produces shrink far below unit length within a few bounces (median |s^2 - 1| = 0.3 at
+// bounce 12 of the 512-sphere lattice), where the inflation alone would make every box of the scene pass.
 // GUARD (a per-scene constant the kernels are instantiated for): 0 = the scene has no spheres, 1 = some
 // subtrees hold spheres (each node says so: kWideHasSpheres), 2 = every node does (an all-sphere scene, or a
 // tree from the GPU builder): the per-node flag test is compiled out.
@@ -96,6 +104,7 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
   s.guard_e = s.guard_lo = 0.f;
   s.box_tmin = s.tmin;
   s.box_tmax_scale = 1.0f;
+  s.sph_clip = x::as_float(0x7F800000u);
   if (GUARD) {
     const float s2 = s.dx * s.dx + s.dy * s.dy + s.dz * s.dz;
     const float inv_s2 = 1.0f / s2;
@@ -103,6 +112,9 @@ HJK_HD void trav_init(TravState& s, const SceneDev& sc, const f4& o_tmin, const 
       s.guard_e = 1.0f - inv_s2;
     } else {
       s.guard_lo = sc.sph_rmax * (sqrtf(inv_s2) - 1.0f);
+      // 1.01: the float evaluation of the discriminant may pass a sphere a few ulps beyond the exact bound
+      const float clip = (2.0f * sqrtf(s2 / (1.0f - s2)) + 1.0f) * sc.sph_rmax * 1.01f;
+      if (clip >= 0.f) s.sph_clip = clip;  // (NaN: no clip)
     }
     if (!(s.guard_e >= 0.f) || !(s.guard_lo >= 0.f))  // NaN / degenerate direction: no culling
       s.guard_lo = x::as_float(0x7F800000u);
@@ -156,7 +168,8 @@ HJK_HD uint32_t intersect_node(const SceneDev& sc, const TravState& s, const f4&
   const float o1x = orgx + infl_x, o1y = orgy + infl_y, o1z = orgz + infl_z;
   const float box_tmin = guarded ? s.box_tmin : s.tmin;
   const float far_t = EXACT ? fminf(s.tmax, s.t_cull) : s.tmax;
-  const float box_tmax = guarded ? far_t * s.box_tmax_scale : far_t;
+  float box_tmax = guarded ? far_t * s.box_tmax_scale : far_t;
+  if (GUARD && guarded && (x::as_uint(q1.y) & kWideOnlySpheres) != 0u) box_tmax = fminf(box_tmax, s.sph_clip);
   const bool nx = s.idx < 0.f, ny = s.idy < 0.f, nz = s.idz < 0.f;
   uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
@@ -329,10 +342,11 @@ HJK_HD void resolve_ties(const SceneDev& sc, TravState& s, TieCands& c, float ep
       c.t[m] = tt, c.id[m] = ii, c.prim[m] = pp;
     }
   }
-  // the cluster ends at the first gap: fl(t[k] - eps) >= t[k-1] means hit k can neither reject nor be
-  // rejected by anything before it
+  // the cluster ends at the first gap: fl(t[k] - eps) >= t[k-1] means hit k, scanned first, cannot make the scan
+  // reject anything before it — unless the two are exactly as far (an eps below one ulp of t leaves fl(t - eps) = t):
+  // then whichever comes later in the scan is accepted over the other, so they still belong together
   uint32_t g = 1;
-  while (g < c.n && !(x::sub(c.t[g], eps) >= c.t[g - 1])) g++;
+  while (g < c.n && (!(x::sub(c.t[g], eps) >= c.t[g - 1]) || c.t[g] == c.t[g - 1])) g++;
   const float window_end = x::add(c.t[0], x::mul(kTieWindowEps, eps));
   if (g == c.n && x::add(c.t[g - 1], eps) > window_end) c.unresolved = 1;  // chain may continue past the window
   if (g == 1u) return;  // the nearest hit stands alone

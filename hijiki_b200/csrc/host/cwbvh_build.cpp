@@ -306,7 +306,8 @@ struct Collapse {  // plain arrays: every entry is written by the sweep, first t
   std::unique_ptr<uint8_t[]> choice;  // 7 per node: i = 1: 0 leaf / 1 inner; i >= 2: k = roots given to
                                       // the left child, 0 = "same as i-1"
   std::unique_ptr<uint8_t[]> root8;   // per node: left share when the node becomes an inner wide node
-  std::unique_ptr<uint8_t[]> has_sphere;  // per node: a sphere among the primitives of its subtree
+  std::unique_ptr<uint8_t[]> has_sphere;  // per node: bit 0 = a sphere, bit 1 = something else among the primitives
+                                          // of its subtree
 };
 
 void collapse_costs(const Binary& bin, uint32_t n_spheres, Collapse& c) {
@@ -326,7 +327,7 @@ void collapse_costs(const Binary& bin, uint32_t n_spheres, Collapse& c) {
         ch[i] = 0;
       }
       c.root8[ni] = 0;
-      c.has_sphere[ni] = bin.order[nd.first] < n_spheres;  // shape index space: spheres first
+      c.has_sphere[ni] = bin.order[nd.first] < n_spheres ? 1 : 2;  // shape index space: spheres first
       return;
     }
     c.has_sphere[ni] = c.has_sphere[nd.left] | c.has_sphere[nd.right];
@@ -663,7 +664,8 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
       scale[k] = std::ldexp(1.0, e);
     }
     wn.child_base = (uint32_t)nodes.size();
-    wn.prim_base = (uint32_t)prims.size() | (col.has_sphere[cur.node2] ? kWideHasSpheres : 0u);
+    wn.prim_base = (uint32_t)prims.size() | ((col.has_sphere[cur.node2] & 1) ? kWideHasSpheres : 0u) |
+                   (col.has_sphere[cur.node2] == 1 ? kWideOnlySpheres : 0u);
     uint32_t prim_off = 0, n_inner = 0;
     for (int sl = 0; sl < 8; sl++) {
       const int c = child_in_slot[sl];

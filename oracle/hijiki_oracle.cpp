@@ -832,9 +832,11 @@ void integrateRay(Ctx& c, Ray ray, uint32_t maxBounces, uint32_t rrStart, PathOu
   Intersection its;
   for (uint32_t bounce = 0; bounce < maxBounces; bounce++) {
     c.nExt++;
+    const float dirLen2 = dot(ray.direction, ray.direction);
     if (!intersectScene(c.s, c.useBvh, c.M_EPS, ray, its)) {
       if (log && *logN < logCap) {
         OrcPathVertex& pv = log[(*logN)++];
+        pv.dir_len2 = dirLen2;
         pv.shape_id = -1;
         pv.t = 0.f;
         pv.rng_after = c.rng.rngState;
@@ -900,6 +902,7 @@ void integrateRay(Ctx& c, Ray ray, uint32_t maxBounces, uint32_t rrStart, PathOu
       pv.throughput[0] = throughput.x, pv.throughput[1] = throughput.y, pv.throughput[2] = throughput.z;
       pv.total[0] = o.total.x, pv.total[1] = o.total.y, pv.total[2] = o.total.z;
       pv.shadow_state = shadowState;
+      pv.dir_len2 = dirLen2;
     }
     if (terminate) break;
     // after an emissive hit `wo` is undefined and throughput is 0; the reference

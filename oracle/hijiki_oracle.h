@@ -74,6 +74,7 @@ typedef struct OrcPathVertex { /* debugging log of one path, one entry per bounc
   float throughput[3];
   float total[3];
   int32_t shadow_state; /* 0 = no shadow ray, 1 = occluded, 2 = unoccluded */
+  float dir_len2;       /* dot(d, d) of the ray that produced this vertex (directions drift off unit length) */
 } OrcPathVertex;
 
 /* rand.glsl:1-20 */

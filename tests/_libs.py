@@ -46,7 +46,8 @@ class OrcStats(C.Structure):
 
 class OrcPathVertex(C.Structure):
     _fields_ = [("shape_id", C.c_int32), ("t", C.c_float), ("rng_after", C.c_uint32),
-                ("throughput", C.c_float * 3), ("total", C.c_float * 3), ("shadow_state", C.c_int32)]
+                ("throughput", C.c_float * 3), ("total", C.c_float * 3), ("shadow_state", C.c_int32),
+                ("dir_len2", C.c_float)]
 
 
 _oracle = None
