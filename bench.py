@@ -420,26 +420,30 @@ def run_workload(rig, wl, steps, warmup, sps, want_e2e, want_exact, sample_clock
     e2e_ms, e2e_rays, result_mean = None, 0, None
     if want_e2e:
         pinned_blocks = [torch.from_numpy(s.view(np.uint8).copy()).pin_memory() for s in slices]
-        out_host = torch.empty((height, width, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+        # two host frames: the copy of step k (hjk_readback_begin, on the library's copy stream) overlaps the
+        # rendering of step k + 1; every step's frame is read back inside the timed region, the last one awaited in it
+        out_host = [torch.empty((height, width, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
 
         def e2e_step(s):
             ctx.frame_begin(width, height)
             st = ctx.render((pinned_blocks[s].data_ptr(), slices[s].size), params)
-            ctx.readback_root_ptr(0, out_host.data_ptr() if rank == 0 else 0, width * 16, normalise=True)
+            ctx.readback_begin_ptr(0, out_host[s & 1].data_ptr() if rank == 0 else 0, width * 16, normalise=True)
             return st.n_rays
 
         for s in range(warmup):
             e2e_step(s)
+        ctx.readback_wait()
         rig.barrier()
         e0, e1 = rig.event(), rig.event()
         e0.record(stream)
         for s in range(warmup, n_steps_total):
             e2e_rays += e2e_step(s)
+        ctx.readback_wait()
         e1.record(stream)
         rig.barrier()
         e2e_ms = e0.elapsed_time(e1)
         if rank == 0:
-            result_mean = float(out_host[..., :3].mean())
+            result_mean = float(out_host[(n_steps_total - 1) & 1][..., :3].mean())
 
     # the path's one collective, timed alone
     reduce_info = None

@@ -101,6 +101,8 @@ _SIGNATURES = {
     "hjk_blocks_free": (C.c_int, [_P, C.c_uint64]),
     "hjk_readback": (C.c_int, [_P, _P, C.c_uint64, C.c_int]),
     "hjk_readback_root": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
+    "hjk_readback_begin": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int]),
+    "hjk_readback_wait": (C.c_int, [_P]),
     "hjk_read_features": (C.c_int, [_P, C.c_int, _P, C.c_uint64]),
     "hjk_read_intermediate": (C.c_int, [_P, C.c_int, _P]),
     "hjk_trace_first_hit": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P, _P]),

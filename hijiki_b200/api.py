@@ -269,6 +269,13 @@ class Context:
     def readback_root_ptr(self, root: int, ptr: int, pitch: int, normalise: bool = True) -> None:
         self._check(self.lib.hjk_readback_root(self.ptr, root, C.c_void_p(ptr) if ptr else None, pitch, int(normalise)))
 
+    def readback_begin_ptr(self, root: int, ptr: int, pitch: int, normalise: bool = True) -> None:
+        """``readback_root_ptr`` without waiting for the copy (``readback_wait`` completes it)."""
+        self._check(self.lib.hjk_readback_begin(self.ptr, root, C.c_void_p(ptr) if ptr else None, pitch, int(normalise)))
+
+    def readback_wait(self) -> None:
+        self._check(self.lib.hjk_readback_wait(self.ptr))
+
     def read_features(self, root: int = -1):
         """Averaged first-hit (normal, depth) of the frame (option ``feature_buffers``), reduced like the frame."""
         if self.get_info("n_ranks") > 1 and self.get_info("n_devices") == 1 and 0 <= root != self.get_info("rank"):

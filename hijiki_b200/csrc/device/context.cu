@@ -129,6 +129,8 @@ struct HjkContext {
   bool has_scene = false;
   SceneDev scene{};
   bool has_extinction = false;
+  bool scene_mixes_materials = false;  // more than one of {diffuse-like, mirror, dielectric} among the shapes
+  int shade_sort = -1;                 // option: -1 = by scene_mixes_materials, 0 / 1 = never / always sort the tiles
   bool bvh_all_guarded = false;  // every node of the wide BVH has a sphere below it (k_trace_coop<2>)
   WideBvh bvh_host_stats;  // nodes/prims cleared after upload; keeps depth etc.
   uint64_t n_nodes = 0, n_prims = 0;
@@ -149,6 +151,10 @@ struct HjkContext {
   f4* feat() const { return (f4*)(d_frame.p + 4 * (size_t)width * height); }
   float* cnt() const { return d_frame.p + 8 * (size_t)width * height; }
   size_t frame_floats() const { return (size_t)width * height * (feature_buffers ? 9 : 4); }
+  // asynchronous readback (hjk_readback_begin / hjk_readback_wait): the staged frame is copied on a stream of its own
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
+  bool copy_pending = false;
   // single-process multi-GPU (hjk_create with n_devices > 1): members[0] is this context, the others own one
   // further device each; every member holds its communicator of ncclCommInitAll in `comm`
   std::vector<HjkContext*> members;
@@ -447,6 +453,7 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   const bool exact = (prm->flags & HJK_RENDER_EXACT_TIES) != 0;
   const bool guard = c->scene.num_spheres != 0;
   const bool use_coop = c->coop_trace && !exact;
+  const bool shade_sort = c->shade_sort < 0 ? c->scene_mixes_materials : c->shade_sort != 0;
   w.stack_cap = use_coop ? c->stack_cap_coop : c->stack_cap_lane;
   const size_t sm_trav = (size_t)w.stack_cap * kTravThreads * sizeof(uint2);
   const int g_trav = grid_for(c, c->blocks_trav_override ? c->blocks_trav_override : c->blocks_trav_v[guard][exact]);
@@ -497,7 +504,10 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
       if (b == last) break;
       {
         KernelTimer t(c, stats, HJK_K_SHADE);
-        k_shade<<<g_tile, kShadeThreads, 0, c->stream>>>(w, b);
+        if (shade_sort)
+          k_shade<true><<<g_tile, kShadeThreads, 0, c->stream>>>(w, b);
+        else
+          k_shade<false><<<g_tile, kShadeThreads, 0, c->stream>>>(w, b);
       }
       launches++;
       if (b + 1 < last && (b + 1) % check_every == 0) {
@@ -726,7 +736,7 @@ static int create_one(int device, HjkContext** out_ctx) {
   cudaEventCreate(&c->ev1);
   trace_launch_shape(c, 7);  // refreshed by every scene upload for the depth of its tree
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade, kShadeThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<true>, kShadeThreads, 0);
   c->blocks_tile = std::max(occ, 1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_raygen, kTileThreads, 0);
   c->blocks_light = std::max(occ, 1);
@@ -759,6 +769,12 @@ static void destroy_one(HjkContext* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->ev_staged);
+    cudaEventDestroy(c->ev_copied);
+  }
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -852,8 +868,10 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   // validate material words and emitter table against the typed arrays they index
   const uint32_t* mats = (const uint32_t*)s->materials.ptr;
   bool has_ext = false;
+  uint32_t classes = 0;  // bit 0 diffuse-like, 1 mirror, 2 dielectric
   for (uint64_t i = 0; i < n_shapes; i++) {
     const uint32_t tag = mats[i] >> HJK_MATERIAL_TAG_SHIFT, idx = mats[i] & ((1u << HJK_MATERIAL_TAG_SHIFT) - 1u);
+    classes |= tag == HJK_MAT_MIRROR ? 2u : tag == HJK_MAT_DIELECTRIC ? 4u : tag == HJK_MAT_EMISSIVE ? 0u : 1u;
     uint64_t limit = 1;
     switch (tag) {
       case HJK_MAT_DIFFUSE: limit = s->diffuse.count; break;
@@ -989,6 +1007,7 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   for (int k = 0; k < 4; k++) d.sph_centre[k] = bvh.sph_centre[k];
   d.sph_rmin = bvh.sph_rmin, d.sph_rmax = bvh.sph_rmax;
   c->has_extinction = has_ext;
+  c->scene_mixes_materials = (classes & (classes - 1u)) != 0u;
   if (keep) *keep = bvh;  // (empty vectors after a GPU build: the other devices of a group then build their own)
   bvh.nodes.clear();
   bvh.nodes.shrink_to_fit();
@@ -1227,22 +1246,53 @@ int hjk_reduce_frame(HjkContext* c, int root, float* out_ms) {
 
 int hjk_allreduce_accumulator(HjkContext* c, float* out_ms) { return hjk_reduce_frame(c, -1, out_ms); }
 
-static int copy_frame_out(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise) {
+// Waits (on the host) for the copy of an earlier hjk_readback_begin.
+static int wait_pending_copy(HjkContext* c) {
+  if (c->copy_pending) {
+    HJK_CUDA(c, cudaEventSynchronize(c->ev_copied));
+    c->copy_pending = false;
+  }
+  return HJK_OK;
+}
+
+// async: the frame is staged in d_norm (normalised, or copied as it is) on the render stream and copied to the host
+// on the copy stream, so the render stream is free for the next frame at once; hjk_readback_wait completes it.
+static int copy_frame_out(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise, bool async) {
   const uint32_t n = c->width * c->height;
   const f4* src = (const f4*)frame_source(c);
+  int rc = wait_pending_copy(c);  // d_norm is about to be rewritten
+  if (rc) return rc;
   if (normalise) {
     HJK_CUDA(c, c->d_norm.ensure(n));
     k_normalise<<<grid_for(c, 4), 256, 0, c->stream>>>(src, c->d_norm.p, n);
     HJK_CUDA(c, cudaGetLastError());
     src = c->d_norm.p;
+  } else if (async) {
+    HJK_CUDA(c, c->d_norm.ensure(n));
+    HJK_CUDA(c, cudaMemcpyAsync(c->d_norm.p, src, (size_t)n * sizeof(f4), cudaMemcpyDeviceToDevice, c->stream));
+    src = c->d_norm.p;
   }
+  if (!async) {
+    HJK_CUDA(c, cudaMemcpy2DAsync(rgba, pitch_bytes, src, (size_t)c->width * 16, (size_t)c->width * 16, c->height,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HJK_OK;
+  }
+  if (!c->copy_stream) {
+    HJK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    HJK_CUDA(c, cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+    HJK_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+  }
+  HJK_CUDA(c, cudaEventRecord(c->ev_staged, c->stream));
+  HJK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_staged, 0));
   HJK_CUDA(c, cudaMemcpy2DAsync(rgba, pitch_bytes, src, (size_t)c->width * 16, (size_t)c->width * 16, c->height,
-                                cudaMemcpyDeviceToHost, c->stream));
-  HJK_CUDA(c, cudaStreamSynchronize(c->stream));
+                                cudaMemcpyDeviceToHost, c->copy_stream));
+  HJK_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+  c->copy_pending = true;
   return HJK_OK;
 }
 
-int hjk_readback_root(HjkContext* c, int root, float* rgba, uint64_t pitch_bytes, int normalise) {
+static int readback_impl(HjkContext* c, int root, float* rgba, uint64_t pitch_bytes, int normalise, bool async) {
   if (!c) return HJK_ERR_INVALID_ARGUMENT;
   if (!c->d_frame.p) return c->fail(HJK_ERR_NO_FRAME, "hjk_readback before any frame");
   const bool multi_rank = c->comm && c->n_ranks > 1 && c->members.size() <= 1;
@@ -1253,7 +1303,21 @@ int hjk_readback_root(HjkContext* c, int root, float* rgba, uint64_t pitch_bytes
   int rc = hjk_reduce_frame(c, root, nullptr);
   if (rc) return rc;
   if (!receives) return HJK_OK;  // the collective is enqueued; this rank's host gets nothing
-  return copy_frame_out(c, rgba, pitch_bytes, normalise);
+  return copy_frame_out(c, rgba, pitch_bytes, normalise, async);
+}
+
+int hjk_readback_root(HjkContext* c, int root, float* rgba, uint64_t pitch_bytes, int normalise) {
+  return readback_impl(c, root, rgba, pitch_bytes, normalise, false);
+}
+
+int hjk_readback_begin(HjkContext* c, int root, float* rgba, uint64_t pitch_bytes, int normalise) {
+  return readback_impl(c, root, rgba, pitch_bytes, normalise, true);
+}
+
+int hjk_readback_wait(HjkContext* c) {
+  if (!c) return HJK_ERR_INVALID_ARGUMENT;
+  HJK_CUDA(c, cudaSetDevice(c->device));
+  return wait_pending_copy(c);
 }
 
 int hjk_readback(HjkContext* c, float* rgba, uint64_t pitch_bytes, int normalise) {
@@ -1530,6 +1594,9 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "bvh_builder") {  // 0 host SAH (default), 1 GPU LBVH; takes effect at the next scene upload
     if (value < 0 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->bvh_builder = (int)value;
+  } else if (k == "shade_sort") {  // -1 = decided per scene (default), 0 = never, 1 = always sort a tile's hits by material
+    if (value < -1 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->shade_sort = (int)value;
   } else if (k == "bvh_validate") {
     c->bvh_validate = value != 0;
   } else if (k == "bvh_broadcast") {  // several ranks: 1 = rank 0 builds and broadcasts the wide BVH (default)
@@ -1567,6 +1634,7 @@ int hjk_get_info(HjkContext* c, const char* key, int64_t* out) {
   else if (k == "blocks_per_sm_tile") *out = c->blocks_tile;
   else if (k == "wave_paths") *out = (int64_t)c->wave_paths;
   else if (k == "has_extinction") *out = c->has_extinction ? 1 : 0;
+  else if (k == "shade_sort") *out = c->shade_sort < 0 ? (c->scene_mixes_materials ? 1 : 0) : c->shade_sort;
   else if (k == "sphere_guard") *out = c->scene.num_spheres ? (c->bvh_all_guarded ? 2 : 1) : 0;
   else if (k == "bvh_builder") *out = c->bvh_builder;
   else if (k == "bvh_build_us") *out = (int64_t)(c->bvh_build_ms * 1000.f);

@@ -571,6 +571,11 @@ __device__ __forceinline__ void shade_tile_front(const WaveDev& w, const uint32_
   }
 }
 
+// SORT: counting-sort the hits of a tile by material tag first, so that a warp shades one material (scenes that mix
+// diffuse, mirror and dielectric surfaces).  Where every surface a path can continue from is diffuse-like (cbox,
+// the terrain) the sort only costs its three barriers and the shared-memory round trip — 12.75 vs 11.82 ms per step
+// on cbox — and each thread shades the hit of its own queue entry instead (hjk_scene_upload decides).
+template <bool SORT>
 __global__ void __launch_bounds__(kShadeThreads, HJK_SHADE_MIN_BLOCKS) k_shade(WaveDev w, uint32_t bounce) {
   __shared__ BlockAppend<2> sm;
   __shared__ TileSort ts;
@@ -585,6 +590,10 @@ __global__ void __launch_bounds__(kShadeThreads, HJK_SHADE_MIN_BLOCKS) k_shade(W
   f4 h = F4(0.f, 0.f, 0.f, 0.f);
   if (blockIdx.x < n_tiles) shade_tile_front(w, q, n, blockIdx.x, bounce, entry, h, tag);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    bool want_next = false, want_shadow = false, shade_this = false;
+    VertexOut out;
+    uint32_t slot = 0, e = 0;
+    if (SORT) {
     // ---- tile-local material sort
     uint32_t prefix = 0;
 #pragma unroll
@@ -616,17 +625,21 @@ __global__ void __launch_bounds__(kShadeThreads, HJK_SHADE_MIN_BLOCKS) k_shade(W
     const uint32_t n_hits = ts.n_hits;
 
     // ---- one bounce-loop iteration per hit
-    bool want_next = false, want_shadow = false;
-    VertexOut out;
-    uint32_t slot = 0;
-    if (threadIdx.x < n_hits) {
+    shade_this = threadIdx.x < n_hits;
+    if (shade_this) {
       entry = ts.entry[threadIdx.x];
+      e = tile * kShadeThreads + ts.src[threadIdx.x];
+      h = ts.hit[threadIdx.x];
+    }
+    } else {  // every thread shades the hit of its own queue entry (misses idle)
+      shade_this = tag < 5u;
+      e = tile * kShadeThreads + threadIdx.x;
+    }
+    if (shade_this) {
       slot = entry & 0x7FFFFFFFu;
-      const uint32_t e = tile * kShadeThreads + ts.src[threadIdx.x];
       VertexIn in;
       in.ray_o = w.ray_o[par][e];
       in.ray_d = w.ray_d[par][e];
-      h = ts.hit[threadIdx.x];
       in.hit_id = __float_as_int(h.x), in.hit_t = h.y, in.hit_u = h.z, in.hit_v = h.w;
       const f4 tr = w.thr_rng[par][e];
       in.throughput = xyz(tr);

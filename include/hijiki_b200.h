@@ -266,6 +266,12 @@ HJK_API int hjk_readback(HjkContext* ctx, float* rgba, uint64_t pitch_bytes, int
  * `rgba` is written, so W*H*16 bytes cross PCIe once per frame, not once per rank.  The other ranks may pass
  * NULL.  root < 0 = hjk_readback. */
 HJK_API int hjk_readback_root(HjkContext* ctx, int root, float* rgba, uint64_t pitch_bytes, int normalise);
+/* hjk_readback_root without the wait: the frame is summed and staged (normalised or raw) on the render stream, and
+ * copied to `rgba` (which should be pinned) on a stream of its own — the call returns as soon as that is enqueued, and
+ * the next hjk_frame_begin / hjk_render can be issued at once, so the copy of frame k overlaps the rendering of frame
+ * k + 1.  `rgba` is complete after hjk_readback_wait (or the next readback call on the context). */
+HJK_API int hjk_readback_begin(HjkContext* ctx, int root, float* rgba, uint64_t pitch_bytes, int normalise);
+HJK_API int hjk_readback_wait(HjkContext* ctx);
 /* Feature buffers of the frame (option "feature_buffers" = 1 before hjk_frame_begin): per texel the mean over
  * its samples of layer 1 = (first-hit normal, depth) (render.glsl:173) — summed by the reconstruction kernel,
  * reduced over ranks/devices together with the accumulator (one collective carries both), divided by the
@@ -342,10 +348,13 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *   "coop_batch_cost"        assumed instructions per pooled batch of 32 tests (default 180; 0 = always pool)
  *   "postpone_lanes"         per-lane k_trace: postpone primitive tests that fewer lanes than this would run
  *                            (default 8)
+ *   "shade_sort"             1 = counting-sort the hits of a shading tile by material so a warp shades one material,
+ *                            0 = shade in queue order, -1 (default) = sort only for scenes that mix diffuse-like,
+ *                            mirror and dielectric surfaces
  *   "blocks_per_sm_traverse", "blocks_per_sm_tile"   persistent-grid sizes
  * Info keys: "n_sms", "bvh_nodes", "bvh_prims", "bvh_depth", "bvh_bytes", "bvh_builder", "bvh_build_us",
  *   "wave_paths", "has_extinction", "sphere_guard" (0 no spheres, 1 per-node flag, 2 every node), "unresolved_ties", "width", "height", "device",
- *   "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_devices", "rank", "n_ranks", "feature_buffers",
+ *   "blocks_per_sm_traverse", "blocks_per_sm_tile", "n_devices", "rank", "n_ranks", "feature_buffers", "shade_sort",
  *   "stack_overflows" (traversal-stack entries that did not fit since the scene upload: must read 0 — the
  *   upload refuses trees deeper than the 32-entry stack and primitive postponing stops short of it). */
 HJK_API int hjk_set_option(HjkContext* ctx, const char* key, int64_t value);

@@ -681,3 +681,48 @@ def test_deep_tree_traversal_stack(gpu_ctx):
         assert diff.sum() <= budget, (flags, int(diff.sum()))
     assert gpu_ctx.get_info("stack_overflows") == 0
     print(f"chain scene: wide BVH depth {depth}, {int((ids_o >= 0).sum())} of {n} probe rays hit, {int(tie.sum())} ties")
+
+
+@pytest.mark.parametrize("kind", ["cbox", "cbox_spheres", "spheres"])
+def test_shade_with_and_without_the_material_sort_agree(gpu_ctx, kind):
+    """k_shade<SORT>: sorting a tile's hits by material only changes which thread shades which hit."""
+    compiled = _compiled(kind)
+    gpu_ctx.scene_upload(compiled)
+    assert gpu_ctx.get_info("shade_sort") == (0 if kind == "cbox" else 1)  # the per-scene default
+    w, h = 136, 100
+    blocks = hj.ImageBlockGenerator(w, h, 64, 3).blocks()
+    frames = []
+    try:
+        for mode in (0, 1):
+            gpu_ctx.set_option("shade_sort", mode)
+            gpu_ctx.frame_begin(w, h)
+            st = gpu_ctx.render(blocks, hj.make_params(max_bounces=12))
+            frames.append((gpu_ctx.readback(normalise=False), st.n_rays))
+    finally:
+        gpu_ctx.set_option("shade_sort", -1)
+    assert frames[0][1] == frames[1][1]
+    assert np.array_equal(frames[0][0].view(np.uint32), frames[1][0].view(np.uint32))
+
+
+def test_asynchronous_readback(gpu_ctx):
+    """hjk_readback_begin / hjk_readback_wait: the staged frame survives the next hjk_frame_begin + hjk_render."""
+    import torch
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h = 200, 120
+    gen = hj.ImageBlockGenerator(w, h, 64, 2)
+    blocks = gen.blocks()
+    first, second = blocks[:gen.blocks_per_pass], blocks[gen.blocks_per_pass:]
+    want = []
+    for part in (first, second):
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.render(np.ascontiguousarray(part), hj.make_params(max_bounces=6))
+        want.append(gpu_ctx.readback(normalise=True))
+    host = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for k, part in enumerate((first, second)):
+        gpu_ctx.frame_begin(w, h)
+        gpu_ctx.render(np.ascontiguousarray(part), hj.make_params(max_bounces=6), want_stats=False)
+        gpu_ctx.readback_begin_ptr(-1, host[k].data_ptr(), w * 16, normalise=True)  # returns before the copy is done
+    gpu_ctx.readback_wait()
+    for k in range(2):
+        assert np.array_equal(host[k].numpy().view(np.uint32), want[k].view(np.uint32))
