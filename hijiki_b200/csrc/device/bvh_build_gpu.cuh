@@ -5,20 +5,22 @@
 //   1. k_shape_boxes   per-shape fp32 boxes (same Bounded rules as host/cwbvh_build.cpp), scene bounds
 //   2. k_morton        outward pad, 63-bit Morton code of the box centre
 //   3. cub::DeviceRadixSort::SortPairs
-//   4. k_radix_tree    binary radix tree over the sorted codes (Karras 2012), one thread per inner node
-//   5. k_fit_boxes     bottom-up box fitting + subtree sizes (second arriver continues upward)
+//   4. k_ploc_*        binary tree by locally-ordered clustering over the Morton order (PLOC, radius 16): SAH-grade
+//                      (option "bvh_gpu_tree" = 0 selects the older pair instead: k_radix_tree, the binary radix
+//                      tree over the sorted codes (Karras 2012), + k_fit_boxes, bottom-up box fitting)
 //   6. k_collapse      level by level: a wide node pulls up to 8 children out of its binary subtree by
 //                      repeatedly opening the child of largest area; subtrees of <= 3 primitives become
 //                      leaves; slots by octant order; 8-bit quantisation rounded outward; primitive
 //                      records written with the reference's separately rounded differences
 //
-// Tree quality is LBVH-grade (no SAH sweep): traversal is slower than with the host builder, so the
-// host builder stays the default; select this one with hjk_set_option("bvh_builder", 1).  Hit results
-// do not depend on the tree (ties excepted), so every parity test also runs against this builder.
+// Select with hjk_set_option("bvh_builder", 1); by default scenes of more than a million shapes use it (the host
+// SAH builder needs seconds there).  Hit results do not depend on the tree (ties excepted), so every parity test
+// also runs against this builder.
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../cwbvh.h"
 #include "scene_dev.cuh"
@@ -213,6 +215,99 @@ __global__ void k_fit_boxes(int n, const uint32_t* vals, const f4* blo, const f4
       node = parent_inner[node];
     }
   }
+}
+
+// ---------------------------------------------------------------- PLOC (parallel locally-ordered clustering)
+// Binary tree by bottom-up agglomeration over the Morton order (Meister & Bittner 2018): every cluster looks for
+// the neighbour within kPlocRadius positions whose union with it has the smallest surface area; mutual nearest
+// neighbours merge; the survivors are compacted (order kept) and the search repeats until one cluster is left.
+// The trees are SAH-grade — unlike the radix tree, whose splits follow the bits of the codes — and the inner
+// nodes come out with their boxes and primitive counts, so no fitting pass is needed.  Inner node ids are handed
+// out so that the root, created last, is node 0 (what k_collapse starts from); everything is deterministic.
+constexpr int kPlocRadius = 16;
+constexpr int kPlocThreads = 256;
+
+__global__ void k_ploc_init(uint32_t n, const uint32_t* vals, const f4* blo, const f4* bhi, uint32_t* ref, f4* clo,
+                            f4* chi, uint32_t* ccnt) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = vals[i];
+    ref[i] = i | kLeafFlag;
+    clo[i] = blo[p];
+    chi[i] = bhi[p];
+    ccnt[i] = 1u;
+  }
+}
+
+// nn[i] = the cluster within kPlocRadius positions of i whose union with i has the smallest area (ties: lower index)
+__global__ void __launch_bounds__(kPlocThreads) k_ploc_nn(uint32_t m, const f4* clo, const f4* chi, uint32_t* nn) {
+  __shared__ f4 slo[kPlocThreads + 2 * kPlocRadius], shi[kPlocThreads + 2 * kPlocRadius];
+  const uint32_t n_tiles = (m + kPlocThreads - 1) / kPlocThreads;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int first = (int)(tile * kPlocThreads) - kPlocRadius;
+    for (int k = threadIdx.x; k < kPlocThreads + 2 * kPlocRadius; k += kPlocThreads) {
+      const int g = first + k;
+      if (g >= 0 && g < (int)m) slo[k] = clo[g], shi[k] = chi[g];
+    }
+    __syncthreads();
+    const int i = (int)(tile * kPlocThreads + threadIdx.x);
+    if (i < (int)m) {
+      const f4 a = slo[threadIdx.x + kPlocRadius], b = shi[threadIdx.x + kPlocRadius];
+      float best = INFINITY;
+      int best_j = -1;
+      const int j0 = max(i - kPlocRadius, 0), j1 = min(i + kPlocRadius, (int)m - 1);
+      for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const f4 c = slo[j - first], d = shi[j - first];
+        const float dx = fmaxf(b.x, d.x) - fminf(a.x, c.x), dy = fmaxf(b.y, d.y) - fminf(a.y, c.y),
+                    dz = fmaxf(b.z, d.z) - fminf(a.z, c.z);
+        const float area = dx * dy + dy * dz + dz * dx;
+        if (area < best) best = area, best_j = j;
+      }
+      nn[i] = (uint32_t)best_j;
+    }
+    __syncthreads();
+  }
+}
+
+// valid[i] = 0 for the member of a mutual pair with the higher index (it is absorbed by its partner)
+__global__ void k_ploc_flags(uint32_t m, const uint32_t* nn, uint32_t* valid) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t j = nn[i];
+    valid[i] = (nn[j] == i && j < i) ? 0u : 1u;
+  }
+}
+
+// state[0] = clusters absorbed so far (= inner nodes created), state[1] = clusters after this round
+__global__ void k_ploc_merge(uint32_t m, uint32_t n, const uint32_t* nn, const uint32_t* valid, const uint32_t* pos,
+                             const uint32_t* ref_in, const f4* lo_in, const f4* hi_in, const uint32_t* cnt_in,
+                             uint32_t* ref_out, f4* lo_out, f4* hi_out, uint32_t* cnt_out, uint32_t* child_l,
+                             uint32_t* child_r, f4* ilo, f4* ihi, uint32_t* icount, const uint32_t* state) {
+  const uint32_t base = state[0];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    if (!valid[i]) continue;
+    const uint32_t j = nn[i];
+    uint32_t r = ref_in[i], c = cnt_in[i];
+    f4 lo = lo_in[i], hi = hi_in[i];
+    if (nn[j] == i && j > i) {  // mutual nearest neighbours: one new inner node
+      const uint32_t rank = base + (j - pos[j]);  // j is the rank-th cluster ever absorbed
+      const uint32_t id = (n - 2u) - rank;        // the last merge creates node 0, the root
+      const f4 lo2 = lo_in[j], hi2 = hi_in[j];
+      lo = F4(fminf(lo.x, lo2.x), fminf(lo.y, lo2.y), fminf(lo.z, lo2.z), 0.f);
+      hi = F4(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z), 0.f);
+      c += cnt_in[j];
+      child_l[id] = r;
+      child_r[id] = ref_in[j];
+      ilo[id] = lo, ihi[id] = hi, icount[id] = c;
+      r = id;
+    }
+    const uint32_t o = pos[i];
+    ref_out[o] = r, lo_out[o] = lo, hi_out[o] = hi, cnt_out[o] = c;
+  }
+}
+__global__ void k_ploc_advance(uint32_t m, const uint32_t* valid, const uint32_t* pos, uint32_t* state) {
+  const uint32_t m_new = pos[m - 1] + valid[m - 1];
+  state[0] += m - m_new;
+  state[1] = m_new;
 }
 
 struct TreeDev {

@@ -94,6 +94,9 @@ struct DevBuf {
 
 thread_local std::string g_create_error;
 
+// scenes with more shapes than this are built on the GPU unless the option "bvh_builder" says otherwise
+constexpr uint64_t kGpuBuilderMinShapes = 1000000;
+
 }  // namespace
 
 struct HjkContext {
@@ -119,7 +122,8 @@ struct HjkContext {
   int blocks_batch = 0;            // k_trace_batch (hjk_trace_first_hit)
   uint32_t stack_cap_coop = 8, stack_cap_lane = 16;  // traversal-stack entries per thread (see trace_launch_shape)
   bool lane_postpones = true;
-  int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU LBVH builder
+  int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU builder, -1 = GPU builder beyond a million shapes
+  int bvh_gpu_tree = 1;  // GPU builder's binary tree: 1 = PLOC (default), 0 = radix tree (LBVH)
   int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
   int bvh_broadcast = 1;  // several ranks: rank 0 builds the wide BVH, the others receive it over ncclBroadcast
   float bvh_build_ms = 0.f;
@@ -601,17 +605,57 @@ int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_r
                                               0, 63, st));
   HJK_CUDA(c, child_l.ensure(n));
   HJK_CUDA(c, child_r.ensure(n));
-  HJK_CUDA(c, parent_inner.ensure(n));
-  HJK_CUDA(c, parent_leaf.ensure(n));
-  HJK_CUDA(c, visits.ensure(n));
   HJK_CUDA(c, icount.ensure(n));
   HJK_CUDA(c, ilo.ensure(n));
   HJK_CUDA(c, ihi.ensure(n));
-  HJK_CUDA(c, cudaMemsetAsync(visits.p, 0, (size_t)n * 4, st));
-  k_radix_tree<<<grid, block, 0, st>>>((int)n, keys_sorted.p, child_l.p, child_r.p, parent_inner.p, parent_leaf.p);
-  k_fit_boxes<<<grid, block, 0, st>>>((int)n, vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, parent_inner.p,
-                                      parent_leaf.p, visits.p, ilo.p, ihi.p, icount.p);
-  HJK_CUDA(c, cudaGetLastError());
+  if (c->bvh_gpu_tree == 0) {  // binary radix tree + bottom-up fitting
+    HJK_CUDA(c, parent_inner.ensure(n));
+    HJK_CUDA(c, parent_leaf.ensure(n));
+    HJK_CUDA(c, visits.ensure(n));
+    HJK_CUDA(c, cudaMemsetAsync(visits.p, 0, (size_t)n * 4, st));
+    k_radix_tree<<<grid, block, 0, st>>>((int)n, keys_sorted.p, child_l.p, child_r.p, parent_inner.p, parent_leaf.p);
+    k_fit_boxes<<<grid, block, 0, st>>>((int)n, vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, parent_inner.p,
+                                        parent_leaf.p, visits.p, ilo.p, ihi.p, icount.p);
+    HJK_CUDA(c, cudaGetLastError());
+  } else {  // PLOC: clusters merge round by round until the root is left (one 4-byte read back per round)
+    DevBuf<uint32_t> ref[2], ccnt[2], nn, valid, pos, state;
+    DevBuf<f4> clo[2], chi[2];
+    DevBuf<uint8_t> scan_tmp;
+    for (int k = 0; k < 2; k++) {
+      HJK_CUDA(c, ref[k].ensure(n));
+      HJK_CUDA(c, ccnt[k].ensure(n));
+      HJK_CUDA(c, clo[k].ensure(n));
+      HJK_CUDA(c, chi[k].ensure(n));
+    }
+    HJK_CUDA(c, nn.ensure(n));
+    HJK_CUDA(c, valid.ensure(n));
+    HJK_CUDA(c, pos.ensure(n));
+    HJK_CUDA(c, state.ensure(2));
+    HJK_CUDA(c, cudaMemsetAsync(state.p, 0, 8, st));
+    size_t scan_bytes = 0;
+    HJK_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, valid.p, pos.p, (int)n, st));
+    HJK_CUDA(c, scan_tmp.ensure(scan_bytes));
+    k_ploc_init<<<grid, block, 0, st>>>(n, vals_sorted.p, blo.p, bhi.p, ref[0].p, clo[0].p, chi[0].p, ccnt[0].p);
+    uint32_t m = n;
+    int cur = 0;
+    for (int round = 0; m > 1; round++) {
+      if (round > 4096) return c->fail(HJK_ERR_CUDA, "PLOC did not converge");
+      const int g_nn = (int)std::min<uint32_t>((m + kPlocThreads - 1) / kPlocThreads, (uint32_t)c->n_sms * 8u);
+      k_ploc_nn<<<g_nn, kPlocThreads, 0, st>>>(m, clo[cur].p, chi[cur].p, nn.p);
+      k_ploc_flags<<<grid, block, 0, st>>>(m, nn.p, valid.p);
+      HJK_CUDA(c, cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, valid.p, pos.p, (int)m, st));
+      k_ploc_merge<<<grid, block, 0, st>>>(m, n, nn.p, valid.p, pos.p, ref[cur].p, clo[cur].p, chi[cur].p, ccnt[cur].p,
+                                           ref[cur ^ 1].p, clo[cur ^ 1].p, chi[cur ^ 1].p, ccnt[cur ^ 1].p, child_l.p,
+                                           child_r.p, ilo.p, ihi.p, icount.p, state.p);
+      k_ploc_advance<<<1, 1, 0, st>>>(m, valid.p, pos.p, state.p);
+      uint32_t st2[2] = {0, 0};
+      HJK_CUDA(c, cudaMemcpyAsync(st2, state.p, 8, cudaMemcpyDeviceToHost, st));
+      HJK_CUDA(c, cudaStreamSynchronize(st));
+      if (st2[1] >= m || st2[1] == 0) return c->fail(HJK_ERR_CUDA, "PLOC made no progress");
+      m = st2[1];
+      cur ^= 1;
+    }
+  }
   const uint32_t node_capacity = n;
   HJK_CUDA(c, tmp_nodes.ensure(node_capacity));
   HJK_CUDA(c, c->d_prims.ensure((size_t)n * HJK_PRIM_STRIDE));
@@ -937,7 +981,9 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
   } else if (bcast && c->rank != 0) {
     // nothing to build: the tree arrives below
   } else {
-    if (c->bvh_builder == 1) {
+    // by default the GPU builder takes the scenes the host builder needs seconds for
+    const bool use_gpu_builder = c->bvh_builder == 1 || (c->bvh_builder < 0 && n_shapes > kGpuBuilderMinShapes);
+    if (use_gpu_builder) {
       rc = build_bvh_gpu(c, info->num_spheres, info->num_quads, info->num_triangles, c->bvh_pad_rel, bvh);
       if (rc == HJK_OK) {
         built_on_gpu = true;
@@ -1033,6 +1079,7 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   for (size_t i = 1; i < c->members.size(); i++) {
     HjkContext* m = c->members[i];
     m->bvh_builder = c->bvh_builder, m->bvh_pad_rel = c->bvh_pad_rel, m->bvh_validate = c->bvh_validate;
+    m->bvh_gpu_tree = c->bvh_gpu_tree;
     rc = scene_upload_impl(m, s, tree.nodes.empty() ? nullptr : &tree, nullptr);
     if (rc) return c->fail(rc, "device %d: %s", m->device, m->error.c_str());
   }
@@ -1591,9 +1638,12 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "coop_batch_cost") {
     if (value < 0 || value > 100000) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->coop_batch_cost = (uint32_t)value;
-  } else if (k == "bvh_builder") {  // 0 host SAH (default), 1 GPU LBVH; takes effect at the next scene upload
-    if (value < 0 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+  } else if (k == "bvh_builder") {  // 0 host SAH (default), 1 GPU, -1 by scene size; takes effect at the next scene upload
+    if (value < -1 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->bvh_builder = (int)value;
+  } else if (k == "bvh_gpu_tree") {  // the GPU builder's binary tree: 1 PLOC (default), 0 radix tree
+    if (value < 0 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->bvh_gpu_tree = (int)value;
   } else if (k == "shade_sort") {  // -1 = decided per scene (default), 0 = never, 1 = always sort a tile's hits by material
     if (value < -1 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->shade_sort = (int)value;

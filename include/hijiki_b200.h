@@ -336,7 +336,10 @@ HJK_API int hjk_set_stream(HjkContext* ctx, void* cuda_stream);
 HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-event timing */
 /* Tuning options (all have measured defaults; none changes results):
  *   "wave_paths"             camera paths rendered per wave (default 64 Mi = 13 GB of path state)
- *   "bvh_builder"            0 = host SAH builder (default), 1 = GPU LBVH builder; next hjk_scene_upload
+ *   "bvh_builder"            0 (default) = host SAH builder, 1 = GPU builder (Morton sort + PLOC clustering + collapse:
+ *                            tens of milliseconds for 10 M triangles, traversal 3-16 % slower), -1 = the host builder up
+ *                            to a million shapes and the GPU builder beyond; takes effect at the next hjk_scene_upload
+ *   "bvh_gpu_tree"           the GPU builder's binary tree: 1 = PLOC (default), 0 = radix tree (LBVH)
  *   "bvh_validate"           1 = run the host structural check on a GPU-built tree
  *   "bvh_broadcast"          several ranks: 1 = rank 0 builds and broadcasts the wide BVH (default), 0 = every rank builds
  *   "feature_buffers"        1 = sum the first-hit (normal, depth) per texel for hjk_read_features (default 0)
