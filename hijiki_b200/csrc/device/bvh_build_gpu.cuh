@@ -37,6 +37,11 @@ struct BuildScene {
 };
 
 constexpr uint32_t kLeafFlag = 0x80000000u;
+// primitive counts of subtrees carry two flag bits on top: a sphere / something other than a sphere lives below
+constexpr uint32_t kCountMask = 0x3FFFFFFFu, kKindSphere = 0x40000000u, kKindOther = 0x80000000u;
+__device__ __forceinline__ uint32_t merge_counts(uint32_t a, uint32_t b) {
+  return ((a & kCountMask) + (b & kCountMask)) | ((a | b) & ~kCountMask);
+}
 
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   const uint32_t u = __float_as_uint(f);
@@ -176,7 +181,7 @@ __global__ void k_radix_tree(int n, const uint64_t* keys, uint32_t* child_l, uin
 }
 
 // One thread per leaf walks up; the second thread to reach an inner node fits its box and goes on.
-__global__ void k_fit_boxes(int n, const uint32_t* vals, const f4* blo, const f4* bhi, const uint32_t* child_l,
+__global__ void k_fit_boxes(int n, uint32_t n_spheres, const uint32_t* vals, const f4* blo, const f4* bhi, const uint32_t* child_l,
                             const uint32_t* child_r, const uint32_t* parent_inner, const uint32_t* parent_leaf,
                             uint32_t* visits, f4* ilo, f4* ihi, uint32_t* icount) {
   for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n; leaf += gridDim.x * blockDim.x) {
@@ -199,19 +204,19 @@ __global__ void k_fit_boxes(int n, const uint32_t* vals, const f4* blo, const f4
       };
       if (cl & kLeafFlag) {
         const uint32_t p = vals[cl & ~kLeafFlag];
-        llo = blo[p], lhi = bhi[p], lc = 1;
+        llo = blo[p], lhi = bhi[p], lc = 1u | (p < n_spheres ? kKindSphere : kKindOther);
       } else {
         load_inner(cl, llo, lhi, lc);
       }
       if (cr & kLeafFlag) {
         const uint32_t p = vals[cr & ~kLeafFlag];
-        rlo = blo[p], rhi = bhi[p], rc = 1;
+        rlo = blo[p], rhi = bhi[p], rc = 1u | (p < n_spheres ? kKindSphere : kKindOther);
       } else {
         load_inner(cr, rlo, rhi, rc);
       }
       ilo[node] = F4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
       ihi[node] = F4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
-      icount[node] = lc + rc;
+      icount[node] = merge_counts(lc, rc);
       node = parent_inner[node];
     }
   }
@@ -224,37 +229,37 @@ __global__ void k_fit_boxes(int n, const uint32_t* vals, const f4* blo, const f4
 // The trees are SAH-grade — unlike the radix tree, whose splits follow the bits of the codes — and the inner
 // nodes come out with their boxes and primitive counts, so no fitting pass is needed.  Inner node ids are handed
 // out so that the root, created last, is node 0 (what k_collapse starts from); everything is deterministic.
-constexpr int kPlocRadius = 16;
+constexpr int kPlocRadius = 16, kPlocMaxRadius = 64;  // default and largest search radius (option "bvh_ploc_radius")
 constexpr int kPlocThreads = 256;
 
-__global__ void k_ploc_init(uint32_t n, const uint32_t* vals, const f4* blo, const f4* bhi, uint32_t* ref, f4* clo,
-                            f4* chi, uint32_t* ccnt) {
+__global__ void k_ploc_init(uint32_t n, uint32_t n_spheres, const uint32_t* vals, const f4* blo, const f4* bhi,
+                            uint32_t* ref, f4* clo, f4* chi, uint32_t* ccnt) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = vals[i];
     ref[i] = i | kLeafFlag;
     clo[i] = blo[p];
     chi[i] = bhi[p];
-    ccnt[i] = 1u;
+    ccnt[i] = 1u | (p < n_spheres ? kKindSphere : kKindOther);
   }
 }
 
-// nn[i] = the cluster within kPlocRadius positions of i whose union with i has the smallest area (ties: lower index)
-__global__ void __launch_bounds__(kPlocThreads) k_ploc_nn(uint32_t m, const f4* clo, const f4* chi, uint32_t* nn) {
-  __shared__ f4 slo[kPlocThreads + 2 * kPlocRadius], shi[kPlocThreads + 2 * kPlocRadius];
+// nn[i] = the cluster within `radius` positions of i whose union with i has the smallest area (ties: lower index)
+__global__ void __launch_bounds__(kPlocThreads) k_ploc_nn(uint32_t m, int radius, const f4* clo, const f4* chi, uint32_t* nn) {
+  __shared__ f4 slo[kPlocThreads + 2 * kPlocMaxRadius], shi[kPlocThreads + 2 * kPlocMaxRadius];
   const uint32_t n_tiles = (m + kPlocThreads - 1) / kPlocThreads;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int first = (int)(tile * kPlocThreads) - kPlocRadius;
-    for (int k = threadIdx.x; k < kPlocThreads + 2 * kPlocRadius; k += kPlocThreads) {
+    const int first = (int)(tile * kPlocThreads) - radius;
+    for (int k = threadIdx.x; k < kPlocThreads + 2 * radius; k += kPlocThreads) {
       const int g = first + k;
       if (g >= 0 && g < (int)m) slo[k] = clo[g], shi[k] = chi[g];
     }
     __syncthreads();
     const int i = (int)(tile * kPlocThreads + threadIdx.x);
     if (i < (int)m) {
-      const f4 a = slo[threadIdx.x + kPlocRadius], b = shi[threadIdx.x + kPlocRadius];
+      const f4 a = slo[threadIdx.x + radius], b = shi[threadIdx.x + radius];
       float best = INFINITY;
       int best_j = -1;
-      const int j0 = max(i - kPlocRadius, 0), j1 = min(i + kPlocRadius, (int)m - 1);
+      const int j0 = max(i - radius, 0), j1 = min(i + radius, (int)m - 1);
       for (int j = j0; j <= j1; j++) {
         if (j == i) continue;
         const f4 c = slo[j - first], d = shi[j - first];
@@ -281,7 +286,8 @@ __global__ void k_ploc_flags(uint32_t m, const uint32_t* nn, uint32_t* valid) {
 __global__ void k_ploc_merge(uint32_t m, uint32_t n, const uint32_t* nn, const uint32_t* valid, const uint32_t* pos,
                              const uint32_t* ref_in, const f4* lo_in, const f4* hi_in, const uint32_t* cnt_in,
                              uint32_t* ref_out, f4* lo_out, f4* hi_out, uint32_t* cnt_out, uint32_t* child_l,
-                             uint32_t* child_r, f4* ilo, f4* ihi, uint32_t* icount, const uint32_t* state) {
+                             uint32_t* child_r, f4* ilo, f4* ihi, uint32_t* icount, uint32_t* parent_inner,
+                             uint32_t* parent_leaf, const uint32_t* state) {
   const uint32_t base = state[0];
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     if (!valid[i]) continue;
@@ -294,10 +300,14 @@ __global__ void k_ploc_merge(uint32_t m, uint32_t n, const uint32_t* nn, const u
       const f4 lo2 = lo_in[j], hi2 = hi_in[j];
       lo = F4(fminf(lo.x, lo2.x), fminf(lo.y, lo2.y), fminf(lo.z, lo2.z), 0.f);
       hi = F4(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z), 0.f);
-      c += cnt_in[j];
+      c = merge_counts(c, cnt_in[j]);
+      const uint32_t r2 = ref_in[j];
       child_l[id] = r;
-      child_r[id] = ref_in[j];
+      child_r[id] = r2;
       ilo[id] = lo, ihi[id] = hi, icount[id] = c;
+      if (r & kLeafFlag) parent_leaf[r & ~kLeafFlag] = id; else parent_inner[r] = id;
+      if (r2 & kLeafFlag) parent_leaf[r2 & ~kLeafFlag] = id; else parent_inner[r2] = id;
+      if (id == 0u) parent_inner[0] = 0xFFFFFFFFu;
       r = id;
     }
     const uint32_t o = pos[i];
@@ -318,7 +328,8 @@ struct TreeDev {
   const uint32_t* child_r;
   const f4* ilo;
   const f4* ihi;
-  const uint32_t* icount;
+  const uint32_t* icount;   // subtree primitive count | kind bits
+  const uint8_t* choice;    // collapse choices of k_collapse_costs, 8 per inner node (nullptr: greedy collapse)
 };
 
 __device__ __forceinline__ void ref_box(const TreeDev& t, uint32_t ref, float lo[3], float hi[3], uint32_t& count) {
@@ -327,7 +338,7 @@ __device__ __forceinline__ void ref_box(const TreeDev& t, uint32_t ref, float lo
     const uint32_t p = t.vals[ref & ~kLeafFlag];
     a = t.blo[p], b = t.bhi[p], count = 1;
   } else {
-    a = t.ilo[ref], b = t.ihi[ref], count = t.icount[ref];
+    a = t.ilo[ref], b = t.ihi[ref], count = t.icount[ref] & kCountMask;
   }
   lo[0] = a.x, lo[1] = a.y, lo[2] = a.z;
   hi[0] = b.x, hi[1] = b.y, hi[2] = b.z;
@@ -367,6 +378,69 @@ __device__ __forceinline__ void write_prim(const BuildScene& s, uint32_t shape, 
   *out = p;
 }
 
+// ---------------------------------------------------------------- collapse costs
+// The dynamic programme of the host builder (cwbvh_build.cpp collapse_costs), bottom-up on the device: cost[n][i-1]
+// = cheapest way to represent the subtree of binary node n as at most i children of a wide node (i = 1..7), with the
+// choice that achieves it; choice[n][7] = how many of a wide node's 8 children go to n's left subtree when n itself
+// becomes an inner wide node.  One thread per leaf walks up; the second thread to reach a node has both children's
+// costs and goes on (as k_fit_boxes).
+constexpr float kCollapseNodeCost = 1.0f, kCollapsePrimCost = 0.3f;
+
+__global__ void k_collapse_costs(int n, const uint32_t* vals, const f4* blo, const f4* bhi, const uint32_t* child_l,
+                                 const uint32_t* child_r, const uint32_t* parent_inner, const uint32_t* parent_leaf,
+                                 const f4* ilo, const f4* ihi, const uint32_t* icount, uint32_t* visits, float* cost,
+                                 uint8_t* choice) {
+  auto half_area = [](f4 lo, f4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    if (!(dx >= 0.f) || !(dy >= 0.f) || !(dz >= 0.f)) return 0.f;
+    return dx * dy + dy * dz + dz * dx;
+  };
+  for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n; leaf += gridDim.x * blockDim.x) {
+    uint32_t node = parent_leaf[leaf];
+    while (node != 0xFFFFFFFFu) {
+      __threadfence();
+      if (atomicAdd(visits + node, 1u) == 0u) break;
+      __threadfence();
+      float c[2][7];
+      const uint32_t refs[2] = {child_l[node], child_r[node]};
+      for (int k = 0; k < 2; k++) {
+        if (refs[k] & kLeafFlag) {
+          const uint32_t p = vals[refs[k] & ~kLeafFlag];
+          const float a = half_area(blo[p], bhi[p]) * kCollapsePrimCost;
+          for (int i = 0; i < 7; i++) c[k][i] = a;
+        } else {
+          const volatile float* src = cost + (size_t)refs[k] * 7;
+          for (int i = 0; i < 7; i++) c[k][i] = src[i];
+        }
+      }
+      const float area = half_area(ilo[node], ihi[node]);
+      const uint32_t count = icount[node] & kCountMask;
+      auto distribute = [&](int j, uint8_t& kbest) {
+        float best = INFINITY;
+        kbest = 1;
+        for (int k = 1; k < j; k++) {
+          const float v = c[0][k - 1] + c[1][j - k - 1];
+          if (v < best) best = v, kbest = (uint8_t)k;
+        }
+        return best;
+      };
+      float cn[7];
+      uint8_t ch[8];
+      const float inner = distribute(8, ch[7]) + area * kCollapseNodeCost;
+      const float as_leaf = count <= kWideMaxLeafPrims ? area * kCollapsePrimCost * (float)count : INFINITY;
+      if (as_leaf <= inner) cn[0] = as_leaf, ch[0] = 0; else cn[0] = inner, ch[0] = 1;
+      for (int i = 2; i <= 7; i++) {
+        uint8_t k;
+        const float d = distribute(i, k);
+        if (d < cn[i - 2]) cn[i - 1] = d, ch[i - 1] = k; else cn[i - 1] = cn[i - 2], ch[i - 1] = 0;
+      }
+      for (int i = 0; i < 7; i++) cost[(size_t)node * 7 + i] = cn[i];
+      for (int i = 0; i < 8; i++) choice[(size_t)node * 8 + i] = ch[i];
+      node = parent_inner[node];
+    }
+  }
+}
+
 // Between two levels of k_collapse: the tasks just emitted become the next level's input; counts the levels
 // that had work (no host round trip per level).  lvl[0] = n_in, lvl[1] = n_out, lvl[2] = depth.
 __global__ void k_next_level(uint32_t* lvl) {
@@ -384,31 +458,59 @@ __global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const
   for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < n_tasks; ti += gridDim.x * blockDim.x) {
     const uint32_t wide = tasks_in[ti].x, root = tasks_in[ti].y;
     uint32_t ref[8], cnt[8];
-    float area[8];
+    bool as_leaf[8];
     float lo[8][3], hi[8][3];
-    int ne = 2;
-    ref[0] = t.child_l[root], ref[1] = t.child_r[root];
-    for (int k = 0; k < 2; k++) {
-      ref_box(t, ref[k], lo[k], hi[k], cnt[k]);
-      const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
-      area[k] = dx * dy + dy * dz + dz * dx;
-    }
-    while (ne < 8) {  // open the largest child that is still a subtree of more than 3 primitives
-      int best = -1;
-      for (int k = 0; k < ne; k++)
-        if (cnt[k] > kWideMaxLeafPrims && (best < 0 || area[k] > area[best])) best = k;
-      if (best < 0) break;
-      const uint32_t r = ref[best];
-      const uint32_t pair[2] = {t.child_l[r], t.child_r[r]};
-      const int at[2] = {best, ne};
-      for (int c = 0; c < 2; c++) {
-        const int k = at[c];
-        ref[k] = pair[c];
+    int ne = 0;
+    if (t.choice) {  // the children the collapse costs chose (cwbvh_build.cpp gather_children)
+      uint32_t st_ref[16];
+      int st_i[16], sp = 0;
+      const int k8 = t.choice[(size_t)root * 8 + 7];
+      st_ref[sp] = t.child_r[root], st_i[sp++] = 8 - k8;
+      st_ref[sp] = t.child_l[root], st_i[sp++] = k8;
+      while (sp > 0 && ne < 8) {
+        const uint32_t r = st_ref[--sp];
+        int ii = st_i[sp];
+        if (r & kLeafFlag) {
+          ref[ne] = r, as_leaf[ne++] = true;
+          continue;
+        }
+        while (ii >= 2 && t.choice[(size_t)r * 8 + ii - 1] == 0) ii--;
+        if (ii == 1) {
+          ref[ne] = r, as_leaf[ne++] = t.choice[(size_t)r * 8] == 0;
+          continue;
+        }
+        const int k = t.choice[(size_t)r * 8 + ii - 1];
+        st_ref[sp] = t.child_r[r], st_i[sp++] = ii - k;
+        st_ref[sp] = t.child_l[r], st_i[sp++] = k;
+      }
+      for (int k = 0; k < ne; k++) ref_box(t, ref[k], lo[k], hi[k], cnt[k]);
+    } else {  // greedy: repeatedly open the child of largest area that is still a subtree of more than 3 primitives
+      float area[8];
+      ne = 2;
+      ref[0] = t.child_l[root], ref[1] = t.child_r[root];
+      for (int k = 0; k < 2; k++) {
         ref_box(t, ref[k], lo[k], hi[k], cnt[k]);
         const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
         area[k] = dx * dy + dy * dz + dz * dx;
       }
-      ne++;
+      while (ne < 8) {
+        int best = -1;
+        for (int k = 0; k < ne; k++)
+          if (cnt[k] > kWideMaxLeafPrims && (best < 0 || area[k] > area[best])) best = k;
+        if (best < 0) break;
+        const uint32_t r = ref[best];
+        const uint32_t pair[2] = {t.child_l[r], t.child_r[r]};
+        const int at[2] = {best, ne};
+        for (int c = 0; c < 2; c++) {
+          const int k = at[c];
+          ref[k] = pair[c];
+          ref_box(t, ref[k], lo[k], hi[k], cnt[k]);
+          const float dx = hi[k][0] - lo[k][0], dy = hi[k][1] - lo[k][1], dz = hi[k][2] - lo[k][2];
+          area[k] = dx * dy + dy * dz + dz * dx;
+        }
+        ne++;
+      }
+      for (int k = 0; k < ne; k++) as_leaf[k] = cnt[k] <= kWideMaxLeafPrims;
     }
     // node box, slot assignment (greedy on sum of dot(child centre - node centre, slot signs))
     float nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -437,7 +539,7 @@ __global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const
     // allocation: inner children contiguous (slot order), primitive records contiguous
     uint32_t n_inner = 0, n_prims = 0;
     for (int k = 0; k < ne; k++) {
-      if (cnt[k] > kWideMaxLeafPrims) n_inner++; else n_prims += cnt[k];
+      if (!as_leaf[k]) n_inner++; else n_prims += cnt[k];
     }
     const uint32_t child_base = n_inner ? atomicAdd(counters + 0, n_inner) : 0u;
     const uint32_t prim_base = n_prims ? atomicAdd(counters + 1, n_prims) : 0u;
@@ -460,8 +562,8 @@ __global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const
     }
     wn.imask = 0;
     wn.child_base = child_base;
-    // no per-subtree knowledge here: all or none
-    wn.prim_base = prim_base | (s.S ? kWideHasSpheres : 0u) | (s.S && !s.Q && !s.T ? kWideOnlySpheres : 0u);
+    const uint32_t kind = t.icount[root] & ~kCountMask;  // what lives below this node
+    wn.prim_base = prim_base | ((kind & kKindSphere) ? kWideHasSpheres : 0u) | (kind == kKindSphere ? kWideOnlySpheres : 0u);
     uint32_t inner_rank = 0, prim_off = 0;
     for (int sl = 0; sl < 8; sl++) {
       const int c = child_in_slot[sl];
@@ -478,7 +580,7 @@ __global__ void k_collapse(BuildScene s, TreeDev t, const uint2* tasks_in, const
         wn.qlo[a][sl] = (uint8_t)ql;
         wn.qhi[a][sl] = (uint8_t)qh;
       }
-      if (cnt[c] > kWideMaxLeafPrims) {
+      if (!as_leaf[c]) {
         wn.meta[sl] = (uint8_t)((1u << 5) | (24u + (uint32_t)sl));
         wn.imask |= (uint8_t)(1u << sl);
         tasks_out[task_base + inner_rank] = make_uint2(child_base + inner_rank, ref[c]);

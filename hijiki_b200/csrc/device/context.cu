@@ -19,6 +19,8 @@
 #include "kernels.cuh"
 
 using namespace hjk;
+using gpubvh::kPlocMaxRadius;
+using gpubvh::kPlocRadius;
 
 namespace {
 
@@ -124,6 +126,8 @@ struct HjkContext {
   bool lane_postpones = true;
   int bvh_builder = 0;   // 0 = host SAH builder (default), 1 = GPU builder, -1 = GPU builder beyond a million shapes
   int bvh_gpu_tree = 1;  // GPU builder's binary tree: 1 = PLOC (default), 0 = radix tree (LBVH)
+  int bvh_ploc_radius = kPlocRadius;
+  int bvh_gpu_collapse = 1;  // GPU builder's wide-node collapse: 1 = collapse-cost dynamic programme, 0 = greedy
   int bvh_validate = 0;  // download the tree after a GPU build and run the host structural check
   int bvh_broadcast = 1;  // several ranks: rank 0 builds the wide BVH, the others receive it over ncclBroadcast
   float bvh_build_ms = 0.f;
@@ -608,13 +612,13 @@ int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_r
   HJK_CUDA(c, icount.ensure(n));
   HJK_CUDA(c, ilo.ensure(n));
   HJK_CUDA(c, ihi.ensure(n));
+  HJK_CUDA(c, parent_inner.ensure(n));
+  HJK_CUDA(c, parent_leaf.ensure(n));
+  HJK_CUDA(c, visits.ensure(n));
   if (c->bvh_gpu_tree == 0) {  // binary radix tree + bottom-up fitting
-    HJK_CUDA(c, parent_inner.ensure(n));
-    HJK_CUDA(c, parent_leaf.ensure(n));
-    HJK_CUDA(c, visits.ensure(n));
     HJK_CUDA(c, cudaMemsetAsync(visits.p, 0, (size_t)n * 4, st));
     k_radix_tree<<<grid, block, 0, st>>>((int)n, keys_sorted.p, child_l.p, child_r.p, parent_inner.p, parent_leaf.p);
-    k_fit_boxes<<<grid, block, 0, st>>>((int)n, vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, parent_inner.p,
+    k_fit_boxes<<<grid, block, 0, st>>>((int)n, S, vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, parent_inner.p,
                                         parent_leaf.p, visits.p, ilo.p, ihi.p, icount.p);
     HJK_CUDA(c, cudaGetLastError());
   } else {  // PLOC: clusters merge round by round until the root is left (one 4-byte read back per round)
@@ -635,18 +639,18 @@ int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_r
     size_t scan_bytes = 0;
     HJK_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, valid.p, pos.p, (int)n, st));
     HJK_CUDA(c, scan_tmp.ensure(scan_bytes));
-    k_ploc_init<<<grid, block, 0, st>>>(n, vals_sorted.p, blo.p, bhi.p, ref[0].p, clo[0].p, chi[0].p, ccnt[0].p);
+    k_ploc_init<<<grid, block, 0, st>>>(n, S, vals_sorted.p, blo.p, bhi.p, ref[0].p, clo[0].p, chi[0].p, ccnt[0].p);
     uint32_t m = n;
     int cur = 0;
     for (int round = 0; m > 1; round++) {
       if (round > 4096) return c->fail(HJK_ERR_CUDA, "PLOC did not converge");
       const int g_nn = (int)std::min<uint32_t>((m + kPlocThreads - 1) / kPlocThreads, (uint32_t)c->n_sms * 8u);
-      k_ploc_nn<<<g_nn, kPlocThreads, 0, st>>>(m, clo[cur].p, chi[cur].p, nn.p);
+      k_ploc_nn<<<g_nn, kPlocThreads, 0, st>>>(m, c->bvh_ploc_radius, clo[cur].p, chi[cur].p, nn.p);
       k_ploc_flags<<<grid, block, 0, st>>>(m, nn.p, valid.p);
       HJK_CUDA(c, cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, valid.p, pos.p, (int)m, st));
       k_ploc_merge<<<grid, block, 0, st>>>(m, n, nn.p, valid.p, pos.p, ref[cur].p, clo[cur].p, chi[cur].p, ccnt[cur].p,
                                            ref[cur ^ 1].p, clo[cur ^ 1].p, chi[cur ^ 1].p, ccnt[cur ^ 1].p, child_l.p,
-                                           child_r.p, ilo.p, ihi.p, icount.p, state.p);
+                                           child_r.p, ilo.p, ihi.p, icount.p, parent_inner.p, parent_leaf.p, state.p);
       k_ploc_advance<<<1, 1, 0, st>>>(m, valid.p, pos.p, state.p);
       uint32_t st2[2] = {0, 0};
       HJK_CUDA(c, cudaMemcpyAsync(st2, state.p, 8, cudaMemcpyDeviceToHost, st));
@@ -663,7 +667,19 @@ int build_bvh_gpu(HjkContext* c, uint32_t S, uint32_t Q, uint32_t T, float pad_r
   HJK_CUDA(c, tasks_b.ensure(n));
   const uint2 root_task = make_uint2(0u, 0u);
   HJK_CUDA(c, cudaMemcpyAsync(tasks_a.p, &root_task, sizeof root_task, cudaMemcpyHostToDevice, st));
-  TreeDev tree{vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, ilo.p, ihi.p, icount.p};
+  // collapse costs (the host builder's dynamic programme), unless the greedy collapse was asked for
+  DevBuf<float> dp_cost;
+  DevBuf<uint8_t> dp_choice;
+  if (c->bvh_gpu_collapse) {
+    HJK_CUDA(c, dp_cost.ensure((size_t)n * 7));
+    HJK_CUDA(c, dp_choice.ensure((size_t)n * 8));
+    HJK_CUDA(c, cudaMemsetAsync(visits.p, 0, (size_t)n * 4, st));
+    k_collapse_costs<<<grid, block, 0, st>>>((int)n, vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, parent_inner.p,
+                                             parent_leaf.p, ilo.p, ihi.p, icount.p, visits.p, dp_cost.p, dp_choice.p);
+    HJK_CUDA(c, cudaGetLastError());
+  }
+  TreeDev tree{vals_sorted.p, blo.p, bhi.p, child_l.p, child_r.p, ilo.p, ihi.p, icount.p,
+               c->bvh_gpu_collapse ? dp_choice.p : nullptr};
   uint2* t_in = tasks_a.p;
   uint2* t_out = tasks_b.p;
   // one launch per level, kMaxStack levels at most, no host round trip in between: a level without tasks is an
@@ -987,7 +1003,8 @@ static int scene_upload_impl(HjkContext* c, const HjkScene* s, const WideBvh* sh
       rc = build_bvh_gpu(c, info->num_spheres, info->num_quads, info->num_triangles, c->bvh_pad_rel, bvh);
       if (rc == HJK_OK) {
         built_on_gpu = true;
-        c->bvh_all_guarded = info->num_spheres != 0;  // the GPU builder flags every node of a scene with spheres
+        // the GPU builder flags its nodes per subtree too; "every node guarded" only holds for all-sphere scenes
+        c->bvh_all_guarded = info->num_spheres != 0 && info->num_quads == 0 && info->num_triangles == 0;
         sphere_guard_bounds(*s, bvh);
         if (c->bvh_validate && !validate_wide_bvh(*s, bvh, err))
           return c->fail(HJK_ERR_CUDA, "GPU-built BVH failed the structural check: %s", err.c_str());
@@ -1079,7 +1096,7 @@ int hjk_scene_upload(HjkContext* c, const HjkScene* s) {
   for (size_t i = 1; i < c->members.size(); i++) {
     HjkContext* m = c->members[i];
     m->bvh_builder = c->bvh_builder, m->bvh_pad_rel = c->bvh_pad_rel, m->bvh_validate = c->bvh_validate;
-    m->bvh_gpu_tree = c->bvh_gpu_tree;
+    m->bvh_gpu_tree = c->bvh_gpu_tree, m->bvh_gpu_collapse = c->bvh_gpu_collapse, m->bvh_ploc_radius = c->bvh_ploc_radius;
     rc = scene_upload_impl(m, s, tree.nodes.empty() ? nullptr : &tree, nullptr);
     if (rc) return c->fail(rc, "device %d: %s", m->device, m->error.c_str());
   }
@@ -1641,6 +1658,11 @@ int hjk_set_option(HjkContext* c, const char* key, int64_t value) {
   } else if (k == "bvh_builder") {  // 0 host SAH (default), 1 GPU, -1 by scene size; takes effect at the next scene upload
     if (value < -1 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->bvh_builder = (int)value;
+  } else if (k == "bvh_gpu_collapse") {  // 1 = the host builder's collapse-cost dynamic programme (default), 0 = greedy
+    c->bvh_gpu_collapse = value != 0;
+  } else if (k == "bvh_ploc_radius") {
+    if (value < 1 || value > kPlocMaxRadius) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
+    c->bvh_ploc_radius = (int)value;
   } else if (k == "bvh_gpu_tree") {  // the GPU builder's binary tree: 1 PLOC (default), 0 radix tree
     if (value < 0 || value > 1) return c->fail(HJK_ERR_INVALID_ARGUMENT, "out of range");
     c->bvh_gpu_tree = (int)value;

@@ -32,6 +32,9 @@ constexpr float kInf = std::numeric_limits<float>::infinity();
 constexpr float kNodeCost = 1.0f;
 constexpr float kPrimCost = 0.3f;
 constexpr int kBins = 16;
+#ifndef HJK_BVH_SWEEP_MAX
+#define HJK_BVH_SWEEP_MAX 2048
+#endif
 
 std::atomic<int> g_builder_threads{0};  // 0 = all
 unsigned builder_threads() {
@@ -138,6 +141,8 @@ struct BinaryBuilder {
   // Nodes over at least this many primitives spread their two passes over the host's threads (min / max
   // and counts: the result does not depend on the chunking).
   static constexpr uint32_t kParallelNode = 1u << 20, kChunk = 1u << 16;
+  static constexpr uint32_t kSweepMax = HJK_BVH_SWEEP_MAX;  // nodes of at most this many primitives: exact SAH sweep
+  static constexpr size_t kSweepSceneMax = 200000;          // ... in scenes of at most this many
 
   // Fills node `ni` (first/count already set); returns false for a leaf, else sets its children.
   bool split(uint32_t ni) {
@@ -170,6 +175,51 @@ struct BinaryBuilder {
     if (count == 1) {
       out.nodes[ni].leaf = true;
       return false;
+    }
+    // small nodes of small scenes: exact SAH sweep — every split position of the centroid order on each axis, not
+    // just the kBins - 1 bin boundaries (cbox: SAH cost 3.95 -> 3.63).  Scenes of millions of primitives keep the
+    // binned sweep everywhere: the terrain's cost does not move and its build would take 70 % longer.
+    if (count <= kSweepMax && boxes.size() <= kSweepSceneMax) {
+      thread_local std::vector<uint32_t> order[3];
+      thread_local std::vector<float> right_area;
+      int best_axis = -1;
+      uint32_t best_pos = 0;
+      float best_cost = kInf;
+      right_area.resize(count);
+      for (int axis = 0; axis < 3; axis++) {
+        if (!(cb.hi[axis] - cb.lo[axis] > 0.f)) continue;
+        std::vector<uint32_t>& o = order[axis];
+        o.assign(idx, idx + count);
+        std::sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) {
+          const float ca = boxes[a].lo[axis] + boxes[a].hi[axis], cb2 = boxes[b].lo[axis] + boxes[b].hi[axis];
+          return ca < cb2 || (ca == cb2 && a < b);
+        });
+        Box acc;
+        acc.reset();
+        for (uint32_t j = count; j-- > 1;) {
+          acc.grow(boxes[o[j]]);
+          right_area[j] = acc.half_area();
+        }
+        acc.reset();
+        for (uint32_t j = 0; j + 1 < count; j++) {  // split after position j
+          acc.grow(boxes[o[j]]);
+          const float cost = acc.half_area() * (float)(j + 1) + right_area[j + 1] * (float)(count - j - 1);
+          if (cost < best_cost) best_cost = cost, best_axis = axis, best_pos = j + 1;
+        }
+      }
+      uint32_t mid = count / 2;
+      if (best_axis >= 0) {
+        std::copy(order[best_axis].begin(), order[best_axis].end(), idx);
+        mid = best_pos;
+      }
+      const uint32_t l = ni + 1, r = ni + 2 * mid;
+      out.nodes[ni].left = l;
+      out.nodes[ni].right = r;
+      out.nodes[l].first = first;
+      out.nodes[l].count = mid;
+      out.nodes[r].first = first + mid;
+      out.nodes[r].count = count - mid;
+      return true;
     }
     // pass 2: binned SAH over the three axes, all three binned in one sweep over the primitives
     float c0[3], scale[3];
