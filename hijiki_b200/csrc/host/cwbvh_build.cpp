@@ -105,6 +105,7 @@ struct Binary {
 struct BinaryBuilder {
   const std::vector<Box>& boxes;
   Binary& out;
+  uint32_t sweep_max;  // nodes of at most this many primitives get the exact SAH sweep (0: binned everywhere)
 
   // Occupied bins only: a node over c primitives touches at most c bins per axis, and most of the 2n-1
   // nodes are tiny, so nothing here costs O(kBins) per node (no reset, no sweep over empty bins).
@@ -141,8 +142,6 @@ struct BinaryBuilder {
   // Nodes over at least this many primitives spread their two passes over the host's threads (min / max
   // and counts: the result does not depend on the chunking).
   static constexpr uint32_t kParallelNode = 1u << 20, kChunk = 1u << 16;
-  static constexpr uint32_t kSweepMax = HJK_BVH_SWEEP_MAX;  // nodes of at most this many primitives: exact SAH sweep
-  static constexpr size_t kSweepSceneMax = 200000;          // ... in scenes of at most this many
 
   // Fills node `ni` (first/count already set); returns false for a leaf, else sets its children.
   bool split(uint32_t ni) {
@@ -179,7 +178,7 @@ struct BinaryBuilder {
     // small nodes of small scenes: exact SAH sweep — every split position of the centroid order on each axis, not
     // just the kBins - 1 bin boundaries (cbox: SAH cost 3.95 -> 3.63).  Scenes of millions of primitives keep the
     // binned sweep everywhere: the terrain's cost does not move and its build would take 70 % longer.
-    if (count <= kSweepMax && boxes.size() <= kSweepSceneMax) {
+    if (count <= sweep_max) {
       thread_local std::vector<uint32_t> order[3];
       thread_local std::vector<float> right_area;
       int best_axis = -1;
@@ -338,11 +337,11 @@ struct BinaryBuilder {
   }
 };
 
-void build_binary(const std::vector<Box>& boxes, Binary& out) {
+void build_binary(const std::vector<Box>& boxes, uint32_t sweep_max, Binary& out) {
   const uint32_t n = (uint32_t)boxes.size();
   out.order.resize(n);
   for (uint32_t i = 0; i < n; i++) out.order[i] = i;
-  BinaryBuilder bb{boxes, out};
+  BinaryBuilder bb{boxes, out, sweep_max};
   out.nodes.assign((size_t)2 * n - 1, Node2());
   out.nodes[0].first = 0;
   out.nodes[0].count = n;
@@ -633,12 +632,26 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
     tick = now;
   };
   lap("primitive boxes");
+  // Small scenes: the top-down build is greedy, so which nodes get the exact sweep changes the tree in ways that are
+  // not monotone in quality — build the candidates (milliseconds each) and keep the one whose collapsed wide tree
+  // is cheapest.  Scenes of more than kSweepSceneMax primitives keep the binned build everywhere: the terrain's
+  // cost does not move with the sweep and its build would take 70 % longer.
+  constexpr size_t kSweepSceneMax = 200000;
+  std::vector<uint32_t> candidates{0u};
+  if (n <= kSweepSceneMax) candidates = {(uint32_t)HJK_BVH_SWEEP_MAX, 0xFFFFFFFFu, 0u};
   Binary bin;
-  build_binary(boxes, bin);
-  lap("binary SAH build");
   Collapse col;
-  collapse_costs(bin, (uint32_t)s.spheres.count, col);
-  lap("collapse costs");
+  for (size_t k = 0; k < candidates.size(); k++) {
+    Binary b2;
+    Collapse c2;
+    build_binary(boxes, candidates[k], b2);
+    collapse_costs(b2, (uint32_t)s.spheres.count, c2);
+    if (k == 0 || c2.cost[0] < col.cost[0]) {
+      bin = std::move(b2);
+      col = std::move(c2);
+    }
+  }
+  lap("binary SAH build + collapse costs");
   out.sah_cost = col.cost[0] / std::max(bin.nodes[0].box.half_area(), 1e-30f);
 
   // Emission.  One wide node at a time: gather its (at most 8) children from the collapse choices,
