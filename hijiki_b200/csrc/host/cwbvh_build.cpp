@@ -721,7 +721,7 @@ void sphere_guard_bounds(const HjkScene& s, WideBvh& out) {
 
 void set_builder_threads(int n) { g_builder_threads.store(n < 0 ? 0 : n); }
 
-bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string& err) {
+static bool build_wide_bvh_impl(const HjkScene& s, float pad_rel, WideBvh& out, std::string& err, bool plain) {
   out = WideBvh();
   const uint64_t S = s.spheres.count, Q = s.quads.count, T = s.triangles.count;
   const uint64_t n64 = S + Q + T;
@@ -785,7 +785,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
   // cost does not move with the sweep and its build would take 70 % longer.
   constexpr size_t kSweepSceneMax = 200000;
   std::vector<uint32_t> candidates{0u};
-  if (n <= kSweepSceneMax) candidates = {(uint32_t)HJK_BVH_SWEEP_MAX, 0xFFFFFFFFu, 0u};
+  if (n <= kSweepSceneMax && !plain) candidates = {(uint32_t)HJK_BVH_SWEEP_MAX, 0xFFFFFFFFu, 0u};
   Binary bin;
   Collapse col;
   bool have = false;
@@ -805,7 +805,7 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
   }
   // ... and the winner once more after insertion-based optimisation (HJK_BVH_REINSERT passes; the default of one
   // takes as long as the three builds together and lowers the cost of cbox by another 1 %)
-  if (n <= kSweepSceneMax) {
+  if (n <= kSweepSceneMax && !plain) {
     static const int passes = [] {
       const char* e = std::getenv("HJK_BVH_REINSERT");
       return e ? std::atoi(e) : 1;
@@ -1009,6 +1009,16 @@ bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string&
 
 // Structural check used by the not-gpu tests: every shape is referenced exactly once, every
 // child box (decoded the way the traversal decodes it) contains the boxes below it.
+
+// The exact sweep can peel an adversarial scene (sizes falling geometrically towards a point) one primitive per
+// split: a tree deeper than the traversal supports (32 levels) is rebuilt with the binned splits only, which halve
+// such a scene's extent per level.
+bool build_wide_bvh(const HjkScene& s, float pad_rel, WideBvh& out, std::string& err) {
+  if (!build_wide_bvh_impl(s, pad_rel, out, err, false)) return false;
+  if (out.depth > 32u) return build_wide_bvh_impl(s, pad_rel, out, err, true);
+  return true;
+}
+
 bool validate_wide_bvh(const HjkScene& s, const WideBvh& bvh, std::string& err) {
   const uint32_t n = bvh.n_shapes;
   std::vector<uint8_t> seen(n, 0);
