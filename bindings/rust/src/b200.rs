@@ -82,6 +82,10 @@ extern "C" {
                                params: *const HjkParams, stats: *mut HjkStats) -> c_int;
     pub fn hjk_blocks_free(ctx: *mut HjkContext, handle: u64) -> c_int;
     pub fn hjk_readback(ctx: *mut HjkContext, rgba: *mut f32, pitch_bytes: u64, normalise: c_int) -> c_int;
+    pub fn hjk_readback_root(ctx: *mut HjkContext, root: c_int, rgba: *mut f32, pitch_bytes: u64, normalise: c_int) -> c_int;
+    pub fn hjk_readback_begin(ctx: *mut HjkContext, root: c_int, rgba: *mut f32, pitch_bytes: u64, normalise: c_int) -> c_int;
+    pub fn hjk_readback_wait(ctx: *mut HjkContext) -> c_int;
+    pub fn hjk_read_features(ctx: *mut HjkContext, root: c_int, normal_depth: *mut f32, pitch_bytes: u64) -> c_int;
     pub fn hjk_read_intermediate(ctx: *mut HjkContext, layer: c_int, rgba: *mut f32) -> c_int;
     pub fn hjk_trace_first_hit(ctx: *mut HjkContext, rays: *const c_void, n_rays: u64, any_hit: c_int,
                                shape_id: *mut i32, t: *mut f32, uv: *mut f32) -> c_int;
@@ -89,6 +93,7 @@ extern "C" {
                             blocks: *const ImageBlock, n_blocks: u64, params: *const HjkParams) -> c_int;
     pub fn hjk_comm_unique_id(out_id128: *mut c_void) -> c_int;
     pub fn hjk_comm_init(ctx: *mut HjkContext, id128: *const c_void, rank: c_int, n_ranks: c_int) -> c_int;
+    pub fn hjk_reduce_frame(ctx: *mut HjkContext, root: c_int, out_ms: *mut f32) -> c_int;
     pub fn hjk_allreduce_accumulator(ctx: *mut HjkContext, out_ms: *mut f32) -> c_int;
     pub fn hjk_accumulator_device_ptr(ctx: *mut HjkContext, out_ptr: *mut u64, out_n_floats: *mut u64) -> c_int;
     pub fn hjk_synchronize(ctx: *mut HjkContext) -> c_int;

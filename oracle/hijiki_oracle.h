@@ -9,8 +9,10 @@
  *
  * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and
  * cannot be built in this image (no Rust, no Vulkan, needs a window).  The oracle is
- * pinned only by the known-answer vectors derived from the reference arithmetic in
- * SURVEY.md §8c (tests/test_oracle_kat.py).  Floating-point conventions the GLSL spec
+ * pinned by the known-answer vectors derived from the reference arithmetic in
+ * SURVEY.md §8c (tests/test_oracle_kat.py) and by a second, independent restatement of whole
+ * paths and of a reconstruction block in numpy float32 (tests/test_oracle_crosscheck.py) —
+ * two restatements agreeing bit for bit, not the reference itself.  Floating-point conventions the GLSL spec
  * leaves open are fixed here: fp32 everywhere, no FMA contraction, IEEE div/sqrt,
  * sin/cos/tan/exp/atan/asin = the fixed polynomial kernels specified in orc_math.h
  * (<= 2 ulp from libm on the ranges the path uses, tests/test_math_spec.py),
