@@ -1159,7 +1159,13 @@ static int render_group(HjkContext* c, const HjkImageBlock* blocks, uint64_t n_b
     p.flags &= ~(uint32_t)HJK_RENDER_ASYNC;  // the block lists above live until the threads join
     rcs[i] = render_blocks(m, lists[i].data(), m->d_blocks.p, lists[i].size(), &p, stats ? &sts[i] : nullptr);
   };
-  for (size_t i = 1; i < n; i++) threads.emplace_back(work, i);
+  for (size_t i = 1; i < n; i++) {
+    try {
+      threads.emplace_back(work, i);
+    } catch (...) {  // no thread to be had: this device's share runs on the calling thread (nothing may throw across the ABI)
+      work(i);
+    }
+  }
   work(0);
   for (std::thread& t : threads) t.join();
   cudaSetDevice(c->device);
@@ -1274,12 +1280,13 @@ static int reduce_group(HjkContext* c, float* out_ms) {
   const size_t n = c->frame_floats();
   HJK_CUDA(c, cudaSetDevice(c->device));
   HJK_CUDA(c, c->d_sum.ensure(9 * (size_t)c->width * c->height));
+  for (HjkContext* m : c->members)
+    if (!m->d_frame.p || m->width != c->width || m->height != c->height)
+      return c->fail(HJK_ERR_NO_FRAME, "device %d has no frame of this size", m->device);
   HJK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   int r = g_nccl.GroupStart();
   for (HjkContext* m : c->members) {
     if (r != 0) break;
-    if (!m->d_frame.p || m->width != c->width || m->height != c->height)
-      return c->fail(HJK_ERR_NO_FRAME, "device %d has no frame of this size", m->device);
     cudaSetDevice(m->device);
     r = g_nccl.Reduce(m->d_frame.p, m == c ? c->d_sum.p : m->d_frame.p, n, 7, 0, 0, m->comm, m->stream);
   }
