@@ -318,9 +318,11 @@ int recon_tensor_map(HjkContext* c, CUtensorMap* tm, const f4* layer, uint32_t w
   return HJK_OK;
 }
 
-int launch_recon(HjkContext* c, const PassDev& ps, uint32_t n_passes, const f4* l0, const f4* l1, const f4* l2,
+int launch_recon(HjkContext* c, const PassDev& ps_in, uint32_t n_passes, const f4* l0, const f4* l1, const f4* l2,
                  f4* acc, bool features) {
-  if (ps.radius < 0 || ps.radius > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
+  if (ps_in.radius < 0 || ps_in.radius > 8) return c->fail(HJK_ERR_UNSUPPORTED, "recon_radius must be in [0, 8]");
+  PassDev ps = ps_in;
+  ps.one = 1.0f;
   const uint32_t layer_stride = recon_layer_stride(ps.radius);  // float4 elements, a multiple of 128 bytes
   const uint32_t stages = n_passes > 1 ? 2u : 1u;
   const size_t smem = (size_t)layer_stride * sizeof(f4) * (l2 ? 3 : 2) * stages;

@@ -780,6 +780,155 @@ __device__ __forceinline__ f4 reconstruct_interior(const uint32_t* tl, uint32_t 
   return acc;
 }
 
+// ---- R = 2 (the reference's radius, src/main.rs:1284) on packed fp32 pairs.  sm_100 executes add/mul/fma on two
+// independent fp32 lanes of a 64-bit register pair (FADD2 / FMUL2 / FFMA2): every lane is the same correctly
+// rounded IEEE operation as its scalar form, so the arithmetic below is reconstruction.glsl's, operation for
+// operation — it only takes fewer issue slots (the kernel is issue-bound: ~930 instructions per texel in scalar
+// form).  Packed: (x, y) and (z, w) of a tap's radiance and normal, as they arrive from one 16-byte shared-memory
+// load, and the bilateral exponential of TWO taps at a time.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pk2(v, v); }
+// 16-byte shared-memory load as two register pairs: (x, y), (z, w)
+__device__ __forceinline__ void lds16x2(uint32_t addr, f32x2& xy, f32x2& zw) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xy), "=l"(zw) : "r"(addr));
+}
+// exp_fma_neg (hjk_math.cuh) of two arguments at once; takes a = -e.  Same operations in the same order per lane.
+__device__ __forceinline__ f32x2 exp_fma_neg2(f32x2 a) {
+  const f32x2 t = fma2(a, splat2(1.44269504088896341f), splat2(12582912.0f));
+  const f32x2 n = add2(t, splat2(-12582912.0f));
+  f32x2 r = fma2(n, splat2(-0.693145751953125f), a);
+  r = fma2(n, splat2(-1.42860682030941723212e-6f), r);
+  f32x2 p = fma2(splat2(1.384070492e-03f), r, splat2(8.368702605e-03f));
+  p = fma2(p, r, splat2(4.166791961e-02f));
+  p = fma2(p, r, splat2(1.666652113e-01f));
+  p = fma2(p, r, splat2(4.999999404e-01f));
+  p = fma2(p, r, splat2(1.0f));
+  const f32x2 y = fma2(p, r, splat2(1.0f));
+  float t0, t1, a0, a1, v0, v1;
+  upk2(t, t0, t1);
+  upk2(a, a0, a1);
+  const f32x2 v = mul2(y, pk2(__uint_as_float((__float_as_uint(t0) << 23) + 0x3F800000u),
+                              __uint_as_float((__float_as_uint(t1) << 23) + 0x3F800000u)));
+  upk2(v, v0, v1);
+  return pk2(a0 < -87.3365402f ? 0.0f : v0, a1 < -87.3365402f ? 0.0f : v1);  // e > cutoff  <=>  -e < -cutoff
+}
+
+// Interior texels of a warp whose 32 texels all lie at least R inside ONE block (k_recon decides: the block is the
+// CTA's, so its tap list is read through warp-uniform addresses and the loop below does not diverge).  The taps of
+// the list are taken two at a time.  No NaN test per tap: a NaN product, which reconstruction.glsl:55-58 drops,
+// is added instead and leaves a NaN in the sum — the caller looks at the sum afterwards and, if it finds one,
+// repeats the texel from the saved accumulator with reconstruct_interior (exact whatever the NaN's origin).
+//   `one` = PassDev::one.  ptxas (12.9) contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 — the scalar
+//   forms with .rn are never contracted, the packed ones are, -fmad=false or not — which would round once where the
+//   reference rounds twice.  The sum is therefore written fma(product, one, acc) with a 1.0 that arrives as a
+//   kernel parameter: x * 1 + acc is exactly acc + x, two multiplies cannot be contracted, and what the compiler
+//   cannot see it cannot simplify back into an add.
+template <bool HAS_ALBEDO>
+struct ReconPairs {
+  uint32_t a0, layer_bytes;
+  f32x2 neg_nc_xy, neg_ac_xy;  // minus the centre features
+  float nc_z, ac_z, one;
+  f32x2 acc_xy, acc_zw;
+
+  // squared distance between the features at `layer_addr` and the centre's
+  __device__ __forceinline__ float dist(uint32_t layer_addr, f32x2 neg_c_xy, float c_z) const {
+    f32x2 n_xy, n_zw;
+    lds16x2(layer_addr, n_xy, n_zw);
+    float nz, nw, sx, sy;
+    upk2(n_zw, nz, nw);
+    const f32x2 d_xy = add2(n_xy, neg_c_xy);  // n - nc = n + (-nc), exactly
+    const float dz = x::sub(nz, c_z);
+    upk2(mul2(d_xy, d_xy), sx, sy);
+    return x::add(x::add(sx, sy), x::mul(dz, dz));
+  }
+  __device__ __forceinline__ void add_products(f32x2 c_xy, f32x2 c_zw, float wt) {
+    const f32x2 ww = splat2(wt), o = splat2(one);
+    acc_xy = fma2(mul2(ww, c_xy), o, acc_xy), acc_zw = fma2(mul2(ww, c_zw), o, acc_zw);
+  }
+  // taps A and B of the list: {spatial weight bits, packed offset}; B == A for the odd one at the end
+  template <bool TWO>
+  __device__ __forceinline__ void pair(uint2 A, uint2 B) {
+    const uint32_t pa = a0 + (uint32_t)((int)A.y >> 16), pb = a0 + (uint32_t)((int)B.y >> 16);
+    f32x2 ca_xy, ca_zw, cb_xy, cb_zw;
+    lds16x2(pa, ca_xy, ca_zw);
+    if (TWO) lds16x2(pb, cb_xy, cb_zw);
+    const float dna = dist(pa + layer_bytes, neg_nc_xy, nc_z), dnb = TWO ? dist(pb + layer_bytes, neg_nc_xy, nc_z) : dna;
+    f32x2 a;  // -e of both taps
+    if (HAS_ALBEDO) {
+      const float daa = dist(pa + 2u * layer_bytes, neg_ac_xy, ac_z);
+      const float dab = TWO ? dist(pb + 2u * layer_bytes, neg_ac_xy, ac_z) : daa;
+      a = mul2(pk2(x::add(x::mul(dna, 2.0f), daa), x::add(x::mul(dnb, 2.0f), dab)), splat2(-1.0f));
+    } else {
+      a = mul2(pk2(dna, dnb), splat2(-2.0f));  // -(2 x) = (-2) x, exactly
+    }
+    float wa, wb;
+    upk2(mul2(pk2(__uint_as_float(A.x), __uint_as_float(B.x)), exp_fma_neg2(a)), wa, wb);
+    add_products(ca_xy, ca_zw, wa);
+    if (TWO) add_products(cb_xy, cb_zw, wb);
+  }
+  __device__ __forceinline__ void run(const uint32_t* tl) {
+    const uint32_t n = tl[0];
+    const uint2* tp = reinterpret_cast<const uint2*>(tl + 2);
+    uint32_t k = 0;
+#pragma unroll 1  // (unrolled twice: 56 instead of 59 instructions per pair, but 20 bytes of spills at 40 registers)
+    for (; k + 1 < n; k += 2) pair<true>(__ldg(tp + k), __ldg(tp + k + 1));
+    if (k < n) {
+      const uint2 A = __ldg(tp + k);
+      pair<false>(A, A);
+    }
+  }
+};
+template <bool HAS_ALBEDO>
+__device__ __forceinline__ f4 reconstruct_interior_pairs(const uint32_t* tl, uint32_t a0, uint32_t layer_bytes, float one,
+                                                         f4 acc) {
+  ReconPairs<HAS_ALBEDO> v;
+  v.layer_bytes = layer_bytes, v.a0 = a0, v.one = one;
+  f32x2 n_xy, n_zw;
+  float nx, ny, nz, nw;
+  lds16x2(a0 + layer_bytes, n_xy, n_zw);
+  upk2(n_xy, nx, ny);
+  upk2(n_zw, nz, nw);
+  v.neg_nc_xy = pk2(-nx, -ny), v.nc_z = nz;
+  v.neg_ac_xy = pk2(-0.f, -0.f), v.ac_z = 0.f;
+  if (HAS_ALBEDO) {
+    lds16x2(a0 + 2u * layer_bytes, n_xy, n_zw);
+    upk2(n_xy, nx, ny);
+    upk2(n_zw, nz, nw);
+    v.neg_ac_xy = pk2(-nx, -ny), v.ac_z = nz;
+  }
+  v.acc_xy = pk2(acc.x, acc.y), v.acc_zw = pk2(acc.z, acc.w);
+  v.run(tl);
+  float ax, ay, az, aw;
+  upk2(v.acc_xy, ax, ay);
+  upk2(v.acc_zw, az, aw);
+  if (ax != ax || ay != ay || az != az || aw != aw)  // a NaN was added (or the accumulator held one): the careful loop decides
+    return reconstruct_interior<HAS_ALBEDO>(tl, a0, layer_bytes, acc);
+  return F4(ax, ay, az, aw);
+}
+
 // ---- TMA plumbing (cp.async.bulk.tensor + mbarrier), sm_90+ PTX written out by hand
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -872,26 +1021,50 @@ __global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS
     const f4* s0 = smem + (size_t)(p & 1u) * NL * layer_stride;
     const f4* s1 = s0 + layer_stride;
     const f4* s2 = s1 + layer_stride;
+    // The block this CTA's tile lies in, when the block grid is a multiple of the tile (the reference's 128 x 128
+    // blocks): known from blockIdx alone, so its tap list is read through uniform addresses.  A warp whose texels all
+    // sit at least R inside that block takes the paired loop; any other warp takes the general path with ALL its
+    // lanes (a warp split between the two would run both, one after the other).
+    bool warp_simple = false;
+    const uint32_t* cta_taps = nullptr;
+    if (RT >= 0 && ps.tile_w % kReconTileX == 0 && ps.tile_h % kReconTileY == 0) {
+      const int32_t cb = ps.tile_block[(blockIdx.y * kReconTileY / ps.tile_h) * ps.tiles_x + blockIdx.x * kReconTileX / ps.tile_w];
+      bool simple = !in_image;
+      if (cb >= 0) {
+        const HjkImageBlock& blk = ps.blocks[cb];
+        const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];
+        simple = simple || (lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
+                            ly + (uint32_t)R < blk.dimension[1]);
+        cta_taps = ps.taps + (size_t)cb * recon_tap_stride(R);
+      } else {
+        simple = false;
+      }
+      warp_simple = __all_sync(0xFFFFFFFFu, simple);
+    }
     if (in_image) {
       if (FEAT) {  // a texel without a sample in this pass holds zeros in both layers (k_raygen)
         const f4 f = s1[cidx];
         feat = F4(x::add(feat.x, f.x), x::add(feat.y, f.y), x::add(feat.z, f.z), x::add(feat.w, f.w));
         cnt = x::add(cnt, s0[cidx].w);
       }
-      const int32_t b = ps.tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
-      bool interior = false;
-      if (b >= 0) {
-        const HjkImageBlock& blk = ps.blocks[b];
-        const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];  // >= 0: block origins sit on the tile grid
-        interior = lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
-                   ly + (uint32_t)R < blk.dimension[1];
-      }
-      if (interior) {
-        acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R),
-                                               smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, acc);
+      if (RT >= 0 && warp_simple) {
+        acc = reconstruct_interior_pairs<HAS_ALBEDO>(cta_taps, smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, ps.one, acc);
       } else {
-        const SmemLayers L{s0, s1, s2, x0, y0, pitch};
-        acc = reconstruct_pixel<HAS_ALBEDO>(ps, L, gx, gy, acc);
+        const int32_t b = ps.tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
+        bool interior = false;
+        if (b >= 0) {
+          const HjkImageBlock& blk = ps.blocks[b];
+          const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];  // >= 0: block origins sit on the tile grid
+          interior = lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
+                     ly + (uint32_t)R < blk.dimension[1];
+        }
+        if (RT < 0 && interior) {  // (RT >= 0: the whole warp stays together on the general path)
+          acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R),
+                                                 smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, acc);
+        } else {
+          const SmemLayers L{s0, s1, s2, x0, y0, pitch};
+          acc = reconstruct_pixel<HAS_ALBEDO>(ps, L, gx, gy, acc);
+        }
       }
     }
     __syncthreads();

@@ -27,6 +27,7 @@ struct PassDev {
                                // int16(16 * (dy * recon_smem_pitch(R) + dx)) << 16: the tap's BYTE offset in
                                // k_recon's shared-memory tile of float4 texels (|.| <= 16 * 392)
   int32_t radius;
+  float one;                   // 1.0f (launch_recon sets it), opaque to the compiler: see ReconPairs (kernels.cuh)
 };
 // pitch of k_recon's shared-memory tile (32 texels + halo); baked into the tap table
 HJK_HD int recon_smem_pitch(int radius) { return 32 + 2 * radius; }
