@@ -304,12 +304,14 @@ EncodeTiledFn encode_tiled_fn() {
 // described as a rank-3 fp32 tensor (4 * width floats per row, height rows, n_passes images) with a box of one
 // tile + halo; out-of-bounds elements read as zero.
 int recon_tensor_map(HjkContext* c, CUtensorMap* tm, const f4* layer, uint32_t width, uint32_t height, uint32_t n_passes,
-                     int radius) {
+                     int radius, bool halo = true) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return c->fail(HJK_ERR_CUDA, "the driver does not export cuTensorMapEncodeTiled");
   const cuuint64_t dims[3] = {4ull * width, height, n_passes};
   const cuuint64_t strides[2] = {16ull * width, 16ull * width * height};  // bytes, dimensions 1 and 2
-  const cuuint32_t box[3] = {4u * (uint32_t)recon_smem_pitch(radius), (uint32_t)(kReconTileY + 2 * radius), 1u};
+  // halo: tile + apron of an intermediate layer; else the bare tile (the accumulator)
+  const cuuint32_t box[3] = {4u * (uint32_t)(halo ? recon_smem_pitch(radius) : kReconTileX),
+                             (uint32_t)(halo ? kReconTileY + 2 * radius : kReconTileY), 1u};
   const cuuint32_t elem_strides[3] = {1u, 1u, 1u};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<f4*>(layer), dims, strides, box, elem_strides,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -324,21 +326,26 @@ int launch_recon(HjkContext* c, const PassDev& ps_in, uint32_t n_passes, const f
   PassDev ps = ps_in;
   ps.one = 1.0f;
   const uint32_t layer_stride = recon_layer_stride(ps.radius);  // float4 elements, a multiple of 128 bytes
-  const uint32_t stages = n_passes > 1 ? 2u : 1u;
-  const size_t smem = (size_t)layer_stride * sizeof(f4) * (l2 ? 3 : 2) * stages;
-  CUtensorMap tm0, tm1, tm2;
+  const uint32_t stages = kReconStages;
+  const size_t smem = ((size_t)layer_stride * (l2 ? 3 : 2) + kReconConsumers) * sizeof(f4) * stages;
+  CUtensorMap tm0, tm1, tm2, tm_acc;
   int rc;
   if ((rc = recon_tensor_map(c, &tm0, l0, ps.width, ps.height, n_passes, ps.radius))) return rc;
   if ((rc = recon_tensor_map(c, &tm1, l1, ps.width, ps.height, n_passes, ps.radius))) return rc;
+  if ((rc = recon_tensor_map(c, &tm_acc, acc, ps.width, ps.height, 1, ps.radius, false))) return rc;
   tm2 = tm1;
   if (l2 && (rc = recon_tensor_map(c, &tm2, l2, ps.width, ps.height, n_passes, ps.radius))) return rc;
-  dim3 block(kReconTileX, kReconTileY);
-  dim3 grid((ps.width + kReconTileX - 1) / kReconTileX, (ps.height + kReconTileY - 1) / kReconTileY);
+  const dim3 block(kReconThreads);
+  const uint32_t tiles_gx = (ps.width + kReconTileX - 1) / kReconTileX;
+  const uint32_t n_tiles = tiles_gx * ((ps.height + kReconTileY - 1) / kReconTileY);
+  // persistent CTAs, as many as fit the device at once (k_recon's launch bound), each taking every grid-th tile
+  const dim3 grid(std::min<uint32_t>(n_tiles, (uint32_t)c->n_sms * HJK_RECON_MIN_BLOCKS));
 #define HJK_RECON(A, RT, F)                                                                                         \
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
       HJK_CUDA(c, cudaFuncSetAttribute(k_recon<A, RT, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_recon<A, RT, F><<<grid, block, smem, c->stream>>>(ps, n_passes, tm0, tm1, tm2, acc, c->feat(), c->cnt());     \
+    k_recon<A, RT, F><<<grid, block, smem, c->stream>>>(ps, n_passes, tiles_gx, n_tiles, tm0, tm1, tm2, tm_acc, acc, \
+                                                        c->feat(), c->cnt());                                       \
   } while (0)
   if (l2) {  // standalone denoise with an albedo layer: no feature sums
     if (ps.radius == 2) HJK_RECON(true, 2, false); else HJK_RECON(true, -1, false);

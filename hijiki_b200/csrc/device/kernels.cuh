@@ -708,8 +708,12 @@ __global__ void k_recon_weights(const HjkImageBlock* blocks, uint32_t n_blocks, 
 #ifndef HJK_RECON_TILE_Y
 #define HJK_RECON_TILE_Y 8
 #endif
+#ifndef HJK_RECON_UNROLL
+#define HJK_RECON_UNROLL 1 /* tap pairs in flight per thread in k_recon's paired loop */
+#endif
+constexpr int kReconUnroll = HJK_RECON_UNROLL;
 #ifndef HJK_RECON_MIN_BLOCKS
-#define HJK_RECON_MIN_BLOCKS 6
+#define HJK_RECON_MIN_BLOCKS 4
 #endif
 constexpr int kReconTileX = 32, kReconTileY = HJK_RECON_TILE_Y;  // recon_smem_pitch() assumes 32
 
@@ -836,19 +840,28 @@ __device__ __forceinline__ f32x2 exp_fma_neg2(f32x2 a) {
   return pk2(a0 < -87.3365402f ? 0.0f : v0, a1 < -87.3365402f ? 0.0f : v1);  // e > cutoff  <=>  -e < -cutoff
 }
 
-// Interior texels of a warp whose 32 texels all lie at least R inside ONE block (k_recon decides: the block is the
-// CTA's, so its tap list is read through warp-uniform addresses and the loop below does not diverge).  The taps of
-// the list are taken two at a time.  No NaN test per tap: a NaN product, which reconstruction.glsl:55-58 drops,
-// is added instead and leaves a NaN in the sum — the caller looks at the sum afterwards and, if it finds one,
-// repeats the texel from the saved accumulator with reconstruct_interior (exact whatever the NaN's origin).
+// One visit of a warp's 32 texels by ONE block (k_recon decides which: the block is warp-uniform, so its tap list
+// is read through uniform addresses and the loop below does not diverge).  The taps of the list are taken two at a
+// time on packed fp32 pairs.
+//   BOUNDS = false: every texel of the warp lies at least R inside the block: all taps of the list count.
+//   BOUNDS = true : a tap counts for a lane when its sample lies inside the block (reconstruction.glsl:41-46); the
+//     lane's position relative to the block is (lx, ly), any value.  A tap that does not count is evaluated on the
+//     tile's dummy texel (finite values) with the weight -0: the products are -0, and x + (-0) = x for every x, so
+//     the lane's sum is untouched without a branch.  A pair no lane needs is skipped (warp vote).
+// No NaN test per tap: a NaN product, which reconstruction.glsl:55-58 drops, is added instead and leaves a NaN in
+// the sum — the caller looks at the sum afterwards and, if it finds one, repeats the texel from the saved
+// accumulator on the careful scalar path (exact whatever the NaN's origin).
 //   `one` = PassDev::one.  ptxas (12.9) contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 — the scalar
 //   forms with .rn are never contracted, the packed ones are, -fmad=false or not — which would round once where the
 //   reference rounds twice.  The sum is therefore written fma(product, one, acc) with a 1.0 that arrives as a
 //   kernel parameter: x * 1 + acc is exactly acc + x, two multiplies cannot be contracted, and what the compiler
 //   cannot see it cannot simplify back into an add.
-template <bool HAS_ALBEDO>
+template <bool HAS_ALBEDO, bool BOUNDS>
 struct ReconPairs {
-  uint32_t a0, layer_bytes;
+  uint32_t a0, layer_bytes;    // shared address of the lane's texel in layer 0; bytes between layers
+  uint32_t dummy;              // shared address of the dummy texel of layer 0 (BOUNDS)
+  int lx128, ly128;            // lx - 128, ly - 128 (the packed tap offset carries dx + 128, dy + 128) (BOUNDS)
+  uint32_t dimx, dimy;         // the block's dimension (BOUNDS)
   f32x2 neg_nc_xy, neg_ac_xy;  // minus the centre features
   float nc_z, ac_z, one;
   f32x2 acc_xy, acc_zw;
@@ -868,10 +881,20 @@ struct ReconPairs {
     const f32x2 ww = splat2(wt), o = splat2(one);
     acc_xy = fma2(mul2(ww, c_xy), o, acc_xy), acc_zw = fma2(mul2(ww, c_zw), o, acc_zw);
   }
-  // taps A and B of the list: {spatial weight bits, packed offset}; B == A for the odd one at the end
+  __device__ __forceinline__ bool counts(uint32_t packed) const {
+    return (uint32_t)(lx128 + (int)(packed & 0xFFu)) < dimx && (uint32_t)(ly128 + (int)((packed >> 8) & 0xFFu)) < dimy;
+  }
+  // taps A and B of the list: {spatial weight bits, packed offset}; TWO = false: A alone (the odd one at the end)
   template <bool TWO>
   __device__ __forceinline__ void pair(uint2 A, uint2 B) {
-    const uint32_t pa = a0 + (uint32_t)((int)A.y >> 16), pb = a0 + (uint32_t)((int)B.y >> 16);
+    uint32_t pa = a0 + (uint32_t)((int)A.y >> 16), pb = a0 + (uint32_t)((int)B.y >> 16);
+    float wsa = __uint_as_float(A.x), wsb = __uint_as_float(B.x);
+    if (BOUNDS) {
+      const bool va = counts(A.y), vb = TWO && counts(B.y);
+      if (!__any_sync(0xFFFFFFFFu, va || vb)) return;
+      if (!va) pa = dummy, wsa = -0.0f;
+      if (!vb) pb = dummy, wsb = -0.0f;
+    }
     f32x2 ca_xy, ca_zw, cb_xy, cb_zw;
     lds16x2(pa, ca_xy, ca_zw);
     if (TWO) lds16x2(pb, cb_xy, cb_zw);
@@ -885,7 +908,7 @@ struct ReconPairs {
       a = mul2(pk2(dna, dnb), splat2(-2.0f));  // -(2 x) = (-2) x, exactly
     }
     float wa, wb;
-    upk2(mul2(pk2(__uint_as_float(A.x), __uint_as_float(B.x)), exp_fma_neg2(a)), wa, wb);
+    upk2(mul2(pk2(wsa, wsb), exp_fma_neg2(a)), wa, wb);
     add_products(ca_xy, ca_zw, wa);
     if (TWO) add_products(cb_xy, cb_zw, wb);
   }
@@ -893,41 +916,38 @@ struct ReconPairs {
     const uint32_t n = tl[0];
     const uint2* tp = reinterpret_cast<const uint2*>(tl + 2);
     uint32_t k = 0;
-#pragma unroll 1  // (unrolled twice: 56 instead of 59 instructions per pair, but 20 bytes of spills at 40 registers)
+#pragma unroll kReconUnroll  // (unrolled twice: 56 instead of 59 instructions per pair, but 20 bytes of spills at 40 registers)
     for (; k + 1 < n; k += 2) pair<true>(__ldg(tp + k), __ldg(tp + k + 1));
     if (k < n) {
       const uint2 A = __ldg(tp + k);
       pair<false>(A, A);
     }
   }
-};
-template <bool HAS_ALBEDO>
-__device__ __forceinline__ f4 reconstruct_interior_pairs(const uint32_t* tl, uint32_t a0, uint32_t layer_bytes, float one,
-                                                         f4 acc) {
-  ReconPairs<HAS_ALBEDO> v;
-  v.layer_bytes = layer_bytes, v.a0 = a0, v.one = one;
-  f32x2 n_xy, n_zw;
-  float nx, ny, nz, nw;
-  lds16x2(a0 + layer_bytes, n_xy, n_zw);
-  upk2(n_xy, nx, ny);
-  upk2(n_zw, nz, nw);
-  v.neg_nc_xy = pk2(-nx, -ny), v.nc_z = nz;
-  v.neg_ac_xy = pk2(-0.f, -0.f), v.ac_z = 0.f;
-  if (HAS_ALBEDO) {
-    lds16x2(a0 + 2u * layer_bytes, n_xy, n_zw);
+  // centre features: the block's own texel, or the zero a robust out-of-bounds load returns for apron texels
+  __device__ __forceinline__ void set_centre(bool inside) {
+    f32x2 n_xy, n_zw;
+    float nx, ny, nz, nw;
+    lds16x2(a0 + layer_bytes, n_xy, n_zw);
     upk2(n_xy, nx, ny);
     upk2(n_zw, nz, nw);
-    v.neg_ac_xy = pk2(-nx, -ny), v.ac_z = nz;
+    neg_nc_xy = inside ? pk2(-nx, -ny) : pk2(-0.f, -0.f), nc_z = inside ? nz : 0.f;
+    neg_ac_xy = pk2(-0.f, -0.f), ac_z = 0.f;
+    if (HAS_ALBEDO) {
+      lds16x2(a0 + 2u * layer_bytes, n_xy, n_zw);
+      upk2(n_xy, nx, ny);
+      upk2(n_zw, nz, nw);
+      neg_ac_xy = inside ? pk2(-nx, -ny) : pk2(-0.f, -0.f), ac_z = inside ? nz : 0.f;
+    }
   }
-  v.acc_xy = pk2(acc.x, acc.y), v.acc_zw = pk2(acc.z, acc.w);
-  v.run(tl);
-  float ax, ay, az, aw;
-  upk2(v.acc_xy, ax, ay);
-  upk2(v.acc_zw, az, aw);
-  if (ax != ax || ay != ay || az != az || aw != aw)  // a NaN was added (or the accumulator held one): the careful loop decides
-    return reconstruct_interior<HAS_ALBEDO>(tl, a0, layer_bytes, acc);
-  return F4(ax, ay, az, aw);
-}
+  __device__ __forceinline__ void set_acc(f4 acc) { acc_xy = pk2(acc.x, acc.y), acc_zw = pk2(acc.z, acc.w); }
+  __device__ __forceinline__ f4 get_acc() const {
+    f4 r;
+    upk2(acc_xy, r.x, r.y);
+    upk2(acc_zw, r.z, r.w);
+    return r;
+  }
+};
+__device__ __forceinline__ bool any_nan(f4 v) { return v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w; }
 
 // ---- TMA plumbing (cp.async.bulk.tensor + mbarrier), sm_90+ PTX written out by hand
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -951,6 +971,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 // box of the rank-3 tensor (floats of a row, rows, passes) at coordinates (c0, c1, c2) -> shared memory; texels
 // outside the image arrive as zeros (the tensor map's out-of-bounds fill), negative coordinates included
 __device__ __forceinline__ void tma_load_box3(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
@@ -960,119 +983,229 @@ __device__ __forceinline__ void tma_load_box3(void* dst, const CUtensorMap* tm, 
       : "memory");
 }
 
-// One launch reconstructs `n_passes` consecutive passes (layers [pass][pixel]): the accumulator texel stays
-// in a register across passes.  Each pass' tile + halo of the two (three) layers is brought into shared
-// memory by the TMA engine — one elected thread issues one box copy per layer, rows outside the image are
-// zero-filled by the copy itself — double-buffered across the fused passes behind two mbarriers: pass p + 1
-// lands while pass p is filtered.  pass_tile_block advances by tiles_x*tiles_y per pass.
-// layer_stride = f4 elements between the layers of a stage (the box rounded up to 128 bytes).
+// One launch reconstructs `n_passes` consecutive passes (layers [pass][pixel]) of the whole frame.
+// PERSISTENT, WARP-SPECIALISED CTAs: CTA c filters the 32 x 8 tiles c, c + gridDim.x, ... and, for each, the passes one
+// after the other, the accumulator texel staying in a register across them.  Warp 8 is the PRODUCER: for every
+// (tile, pass) item it has the TMA engine bring the tile + halo of the two (three) layers into one of kReconStages
+// shared-memory stages — one box copy per layer, texels outside the image zero-filled by the copy itself — and
+// writes the item's description next to it (tile origin, the block the tile lies in: everything the eight CONSUMER
+// warps would otherwise each derive with integer divisions and two dependent global loads).  full/empty mbarriers per
+// stage: the producer runs up to kReconStages items ahead, across passes AND across tiles, and a consumer warp that
+// is done with an item moves on without waiting for the CTA's slowest warp (a warp on a block edge does 2-3 times
+// the work of an interior one).
+// layer_stride = f4 elements between the layers of a stage: the box, one dummy texel, rounded up to 128 bytes; the
+// accumulator texels of the tile travel with the first pass of every tile (a fourth box copy into the stage).
 // RT = the filter radius when it is a compile-time constant (2, the reference's: src/main.rs:1284), else -1.
-HJK_HD uint32_t recon_layer_stride(int radius) {  // a layer's box in float4 elements, rounded up to 128 bytes
-  return ((uint32_t)(recon_smem_pitch(radius) * (kReconTileY + 2 * radius)) + 7u) & ~7u;
+#ifndef HJK_RECON_STAGES
+#define HJK_RECON_STAGES 3
+#endif
+constexpr uint32_t kReconStages = HJK_RECON_STAGES;
+constexpr int kReconConsumers = kReconTileX * kReconTileY;  // threads; one more warp produces
+constexpr int kReconThreads = kReconConsumers + 32;
+HJK_HD uint32_t recon_layer_stride(int radius) {
+  return ((uint32_t)(recon_smem_pitch(radius) * (kReconTileY + 2 * radius)) + 1u + 7u) & ~7u;
 }
+struct alignas(16) ReconItem {
+  int32_t tox, toy;      // image coordinate of the tile's first texel
+  int32_t cb;            // the block the whole tile lies in (block grid a multiple of the tile), else -1
+  uint32_t pass;         // pass index | kReconFirst | kReconLast
+  int32_t box, boy;      // that block's origin,
+  uint32_t bdx, bdy;     //   dimension
+  int32_t btx, bty;      //   and position in the block grid
+};
+constexpr uint32_t kReconFirst = 0x40000000u, kReconLast = 0x80000000u;
 // FEAT: also sum the texel's own first-hit features over the passes (feature_sum += (normal, depth),
 // sample_count += layer 0's w) — the averaged feature buffers a multi-GPU frame reduces with the accumulator.
 template <bool HAS_ALBEDO, int RT, bool FEAT>
-__global__ void __launch_bounds__(kReconTileX* kReconTileY, HJK_RECON_MIN_BLOCKS)
-    k_recon(PassDev ps, uint32_t n_passes, const __grid_constant__ CUtensorMap tm0,
+__global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
+    k_recon(PassDev ps, uint32_t n_passes, uint32_t tiles_gx, uint32_t n_tiles, const __grid_constant__ CUtensorMap tm0,
             const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-            f4* __restrict__ accumulator, f4* __restrict__ feature_sum, float* __restrict__ sample_count) {
+            const __grid_constant__ CUtensorMap tm_acc, f4* __restrict__ accumulator, f4* __restrict__ feature_sum,
+            float* __restrict__ sample_count) {
   extern __shared__ __align__(128) f4 smem[];
-  __shared__ uint64_t full[2];
+  __shared__ uint64_t full[kReconStages], empty[kReconStages];
+  __shared__ ReconItem items[kReconStages];
   constexpr uint32_t NL = HAS_ALBEDO ? 3u : 2u;
   const int R = RT >= 0 ? RT : ps.radius;
   const int pitch = recon_smem_pitch(R), rows = kReconTileY + 2 * R;
   const uint32_t layer_stride = recon_layer_stride(R);
-  const int x0 = (int)blockIdx.x * kReconTileX - R, y0 = (int)blockIdx.y * kReconTileY - R;
-  // a warp covers 4 x 8 texels, not 32 x 1: texels within R of a block edge run a second (or
-  // fourth) block's tap list, and narrow warps keep those few texels from stalling 28 others
-  const int tid = threadIdx.y * kReconTileX + threadIdx.x;
+  const uint32_t stage_stride = NL * layer_stride + kReconConsumers;  // f4 elements: the layers, then the tile's accumulator texels
+  const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const uint32_t gx = blockIdx.x * kReconTileX + 4u * (warp & 7) + (lane & 3);
-  const uint32_t gy = blockIdx.y * kReconTileY + 8u * (warp >> 3) + (lane >> 2);
-  const bool in_image = gx < ps.width && gy < ps.height;
-  const uint32_t tx_bytes = (uint32_t)(pitch * rows) * 16u * NL;
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (uint32_t st = 0; st < kReconStages; st++) mbar_init(&full[st], 1), mbar_init(&empty[st], kReconConsumers / 32);
     mbar_init_fence();
   }
+  if ((uint32_t)tid < kReconStages * NL)  // the dummy texel behind every layer's box (ReconPairs): finite features, radiance 1
+    smem[(size_t)((uint32_t)tid / NL) * stage_stride + (size_t)((uint32_t)tid % NL) * layer_stride + (size_t)(pitch * rows)] = F4(1.f, 1.f, 1.f, 1.f);
   __syncthreads();
-  auto issue = [&](uint32_t p) {  // thread 0: stage p & 1 <- tile + halo of pass p
-    f4* dst = smem + (size_t)(p & 1u) * NL * layer_stride;
-    uint64_t* bar = &full[p & 1u];
-    mbar_expect_tx(bar, tx_bytes);
-    tma_load_box3(dst, &tm0, bar, 4 * x0, y0, (int)p);
-    tma_load_box3(dst + layer_stride, &tm1, bar, 4 * x0, y0, (int)p);
-    if (HAS_ALBEDO) tma_load_box3(dst + 2 * layer_stride, &tm2, bar, 4 * x0, y0, (int)p);
-  };
-  if (tid == 0) issue(0);
+  const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  const uint32_t n_items = my_tiles * n_passes;
+  const size_t pass_tiles = (size_t)ps.tiles_x * ps.tiles_y;
+  const bool aligned = RT >= 0 && ps.tile_w % kReconTileX == 0 && ps.tile_h % kReconTileY == 0;
+
+  if (warp == kReconConsumers / 32) {  // ---------------------------------------------------------------- producer
+    // 32 items at a time: every lane derives one item's description (two dependent global loads: all in flight at
+    // once), then the lanes take turns issuing their item, so that an item costs the producer no memory round trip
+    const uint32_t tx_bytes = (uint32_t)(pitch * rows) * 16u * NL;
+    uint32_t st = 0, use = 0;
+    for (uint32_t base = 0; base < n_items; base += 32u) {
+      const uint32_t j = base + (uint32_t)lane;
+      const uint32_t tile = blockIdx.x + (j / n_passes) * gridDim.x, pass = j % n_passes;
+      // tiles are numbered column by column: the tiles c, c + gridDim.x, ... of a CTA then fall on every position
+      // inside a block (row-major, with 4 tiles per block row and a grid that is a multiple of 4, half of the CTAs
+      // would get nothing but tiles on a block's left or right edge: 20 % more work than the others)
+      const uint32_t tiles_gy = n_tiles / tiles_gx;
+      const uint32_t tbx = tile / tiles_gy, tby = tile % tiles_gy;
+      const bool last = pass + 1 == n_passes;
+      ReconItem it;
+      it.tox = (int32_t)(tbx * kReconTileX), it.toy = (int32_t)(tby * kReconTileY);
+      it.pass = pass | (pass == 0 ? kReconFirst : 0u) | (last ? kReconLast : 0u);
+      it.cb = -1, it.box = it.boy = 0, it.bdx = it.bdy = 0, it.btx = it.bty = 0;
+      if (aligned && j < n_items) {
+        it.btx = (int32_t)(tbx * kReconTileX / ps.tile_w), it.bty = (int32_t)(tby * kReconTileY / ps.tile_h);
+        it.cb = ps.tile_block[(size_t)pass * pass_tiles + (size_t)it.bty * ps.tiles_x + it.btx];
+        if (it.cb >= 0) {
+          const HjkImageBlock& blk = ps.blocks[it.cb];
+          it.box = (int32_t)blk.origin[0], it.boy = (int32_t)blk.origin[1];
+          it.bdx = blk.dimension[0], it.bdy = blk.dimension[1];
+        }
+      }
+      const uint32_t n_here = n_items - base < 32u ? n_items - base : 32u;
+      for (uint32_t l = 0; l < n_here; l++) {
+        if ((uint32_t)lane == l) {
+          if (use) mbar_wait(&empty[st], (use - 1u) & 1u);  // every consumer warp is done with the stage's previous item
+          const int x0 = it.tox - R, y0 = it.toy - R;
+          f4* dst = smem + (size_t)st * stage_stride;
+          tma_load_box3(dst, &tm0, &full[st], 4 * x0, y0, (int)pass);
+          tma_load_box3(dst + layer_stride, &tm1, &full[st], 4 * x0, y0, (int)pass);
+          if (HAS_ALBEDO) tma_load_box3(dst + 2 * layer_stride, &tm2, &full[st], 4 * x0, y0, (int)pass);
+          if (pass == 0) tma_load_box3(dst + NL * layer_stride, &tm_acc, &full[st], 4 * it.tox, it.toy, 0);
+          items[st] = it;
+          // the stage's one arrival (release: the description is visible with it)
+          mbar_expect_tx(&full[st], tx_bytes + (pass == 0 ? (uint32_t)kReconConsumers * 16u : 0u));
+        }
+        __syncwarp();
+        if (++st == kReconStages) st = 0, use++;
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------------------------------------------- consumers
+  // a warp covers 4 x 8 texels, not 32 x 1: the fewest warps touch a block edge that way
+  // Which rectangle a warp takes rotates from tile to tile: the rectangle on a block edge costs 2-3 times the
+  // others and sits at the same place in every tile of a block column, so a fixed assignment would leave seven warps
+  // waiting for the eighth; rotated, the pipeline's stages absorb it.
+  static_assert(kReconTileY == 8 && kReconTileX == 32, "8 warp rectangles of 4 x 8 texels");
+  uint32_t wx = 0, tx_in = 0;
+  const uint32_t wy = 0, ty_in = (uint32_t)lane >> 2;
+  int cidx = 0;
   f4 acc = F4(0.f, 0.f, 0.f, 0.f), feat = acc;
   float cnt = 0.f;
-  if (in_image) {
-    acc = accumulator[(size_t)gy * ps.width + gx];
-    if (FEAT) feat = feature_sum[(size_t)gy * ps.width + gx], cnt = sample_count[(size_t)gy * ps.width + gx];
-  }
-  const int cidx = ((int)gy - y0) * pitch + ((int)gx - x0);
-  for (uint32_t p = 0; p < n_passes; p++) {
-    // stage (p + 1) & 1 was last read in iteration p - 1, which ended with a CTA barrier
-    if (tid == 0 && p + 1 < n_passes) issue(p + 1);
-    mbar_wait(&full[p & 1u], (p >> 1) & 1u);
-    const f4* s0 = smem + (size_t)(p & 1u) * NL * layer_stride;
+  uint32_t gx = 0, gy = 0, st = 0, use = 0;
+  bool in_image = false;
+  for (uint32_t j = 0; j < n_items; j++) {
+    mbar_wait(&full[st], use & 1u);
+    const ReconItem& it = items[st];  // (left in shared memory: fields are read where they are used)
+    const uint32_t pass = it.pass & 0x3FFFFFFFu;
+    if (it.pass & kReconFirst) {
+      wx = 4u * (((uint32_t)warp + j / n_passes) & 7u), tx_in = wx + ((uint32_t)lane & 3u);
+      cidx = ((int)ty_in + R) * pitch + ((int)tx_in + R);
+      gx = (uint32_t)it.tox + tx_in, gy = (uint32_t)it.toy + ty_in;
+      in_image = gx < ps.width && gy < ps.height;
+      acc = smem[(size_t)st * stage_stride + NL * layer_stride + ty_in * kReconTileX + tx_in];  // came with the stage
+      if (FEAT && in_image) feat = feature_sum[(size_t)gy * ps.width + gx], cnt = sample_count[(size_t)gy * ps.width + gx];
+    }
+    const f4* s0 = smem + (size_t)st * stage_stride;
     const f4* s1 = s0 + layer_stride;
     const f4* s2 = s1 + layer_stride;
-    // The block this CTA's tile lies in, when the block grid is a multiple of the tile (the reference's 128 x 128
-    // blocks): known from blockIdx alone, so its tap list is read through uniform addresses.  A warp whose texels all
-    // sit at least R inside that block takes the paired loop; any other warp takes the general path with ALL its
-    // lanes (a warp split between the two would run both, one after the other).
-    bool warp_simple = false;
-    const uint32_t* cta_taps = nullptr;
-    if (RT >= 0 && ps.tile_w % kReconTileX == 0 && ps.tile_h % kReconTileY == 0) {
-      const int32_t cb = ps.tile_block[(blockIdx.y * kReconTileY / ps.tile_h) * ps.tiles_x + blockIdx.x * kReconTileX / ps.tile_w];
-      bool simple = !in_image;
-      if (cb >= 0) {
-        const HjkImageBlock& blk = ps.blocks[cb];
-        const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];
-        simple = simple || (lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
-                            ly + (uint32_t)R < blk.dimension[1]);
-        cta_taps = ps.taps + (size_t)cb * recon_tap_stride(R);
-      } else {
-        simple = false;
-      }
-      warp_simple = __all_sync(0xFFFFFFFFu, simple);
+    const int x0 = it.tox - R, y0 = it.toy - R;
+    const int32_t* tile_block = ps.tile_block + (size_t)pass * pass_tiles;
+    if (FEAT && in_image) {  // a texel without a sample in this pass holds zeros in both layers (k_raygen)
+      const f4 f = s1[cidx];
+      feat = F4(x::add(feat.x, f.x), x::add(feat.y, f.y), x::add(feat.z, f.z), x::add(feat.w, f.w));
+      cnt = x::add(cnt, s0[cidx].w);
     }
-    if (in_image) {
-      if (FEAT) {  // a texel without a sample in this pass holds zeros in both layers (k_raygen)
-        const f4 f = s1[cidx];
-        feat = F4(x::add(feat.x, f.x), x::add(feat.y, f.y), x::add(feat.z, f.z), x::add(feat.w, f.w));
-        cnt = x::add(cnt, s0[cidx].w);
-      }
-      if (RT >= 0 && warp_simple) {
-        acc = reconstruct_interior_pairs<HAS_ALBEDO>(cta_taps, smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, ps.one, acc);
+    // it.cb = the block the tile lies in (block grid a multiple of the tile: the reference's 128 x 128 blocks).  All 32
+    // lanes of a warp stay together: either every texel of the warp sits at least R inside that block (one visit,
+    // every tap counts), or the warp visits, in block-list order, every block whose apron reaches its 4 x 8
+    // rectangle, each lane counting the taps whose samples lie inside the visited block.
+    if (RT >= 0 && it.cb >= 0) {
+      const uint32_t a0 = smem_addr(s0) + (uint32_t)cidx * 16u, layer_bytes = layer_stride * 16u;
+      const uint32_t ox = (uint32_t)(it.tox - it.box) + wx, oy = (uint32_t)(it.toy - it.boy) + wy;  // the rectangle in the block
+      const bool interior = ox >= (uint32_t)R && oy >= (uint32_t)R && ox + 3u + (uint32_t)R < it.bdx && oy + 7u + (uint32_t)R < it.bdy;
+      f4 r;
+      if (interior) {
+        ReconPairs<HAS_ALBEDO, false> v;
+        v.a0 = a0, v.layer_bytes = layer_bytes, v.one = ps.one;
+        v.set_centre(true);
+        v.set_acc(acc);
+        v.run(ps.taps + (size_t)it.cb * recon_tap_stride(R));
+        r = v.get_acc();
       } else {
-        const int32_t b = ps.tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
-        bool interior = false;
-        if (b >= 0) {
-          const HjkImageBlock& blk = ps.blocks[b];
-          const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];  // >= 0: block origins sit on the tile grid
-          interior = lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
-                     ly + (uint32_t)R < blk.dimension[1];
+        ReconPairs<HAS_ALBEDO, true> v;
+        v.a0 = a0, v.layer_bytes = layer_bytes, v.one = ps.one;
+        v.dummy = smem_addr(s0) + (uint32_t)(pitch * rows) * 16u;
+        v.set_acc(acc);
+        // blocks that can hold a sample within R of the rectangle: the own one and its neighbours in the block grid
+        // (blocks sit on the grid: the own block's origin is (btx * tile_w, bty * tile_h))
+        int tx0 = it.btx - (ox < (uint32_t)R ? 1 : 0), ty0 = it.bty - (oy < (uint32_t)R ? 1 : 0);
+        int tx1 = it.btx + (ox + 3u + (uint32_t)R >= ps.tile_w ? 1 : 0), ty1 = it.bty + (oy + 7u + (uint32_t)R >= ps.tile_h ? 1 : 0);
+        if (tx0 < 0) tx0 = 0;
+        if (ty0 < 0) ty0 = 0;
+        if (tx1 >= (int)ps.tiles_x) tx1 = (int)ps.tiles_x - 1;
+        if (ty1 >= (int)ps.tiles_y) ty1 = (int)ps.tiles_y - 1;
+        for (int by = ty0; by <= ty1; by++) {
+          for (int bx = tx0; bx <= tx1; bx++) {
+            const int32_t b = tile_block[by * (int)ps.tiles_x + bx];
+            if (b < 0) continue;
+            const HjkImageBlock& blk = ps.blocks[b];
+            const int lx = (int)gx - (int)blk.origin[0], ly = (int)gy - (int)blk.origin[1];
+            v.dimx = blk.dimension[0], v.dimy = blk.dimension[1];
+            // a lane outside the image counts no tap
+            v.lx128 = in_image ? lx - 128 : (int)0x80000000, v.ly128 = ly - 128;
+            v.set_centre((uint32_t)lx < v.dimx && (uint32_t)ly < v.dimy);
+            v.run(ps.taps + (size_t)b * recon_tap_stride(R));
+          }
         }
-        if (RT < 0 && interior) {  // (RT >= 0: the whole warp stays together on the general path)
-          acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R),
-                                                 smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, acc);
-        } else {
+        r = v.get_acc();
+      }
+      if (in_image) {
+        if (any_nan(r)) {  // a NaN was added (or the accumulator held one): the careful path decides
           const SmemLayers L{s0, s1, s2, x0, y0, pitch};
-          acc = reconstruct_pixel<HAS_ALBEDO>(ps, L, gx, gy, acc);
+          PassDev pp = ps;
+          pp.tile_block = tile_block;
+          r = reconstruct_pixel<HAS_ALBEDO>(pp, L, gx, gy, acc);
         }
+        acc = r;
+      }
+    } else if (in_image) {
+      const int32_t b = tile_block[(gy / ps.tile_h) * ps.tiles_x + gx / ps.tile_w];
+      bool interior = false;
+      if (b >= 0) {
+        const HjkImageBlock& blk = ps.blocks[b];
+        const uint32_t lx = gx - blk.origin[0], ly = gy - blk.origin[1];  // >= 0: block origins sit on the tile grid
+        interior = lx >= (uint32_t)R && ly >= (uint32_t)R && lx + (uint32_t)R < blk.dimension[0] &&
+                   ly + (uint32_t)R < blk.dimension[1];
+      }
+      if (interior) {
+        acc = reconstruct_interior<HAS_ALBEDO>(ps.taps + (size_t)b * recon_tap_stride(R),
+                                               smem_addr(s0) + (uint32_t)cidx * 16u, layer_stride * 16u, acc);
+      } else {
+        const SmemLayers L{s0, s1, s2, x0, y0, pitch};
+        PassDev pp = ps;
+        pp.tile_block = tile_block;
+        acc = reconstruct_pixel<HAS_ALBEDO>(pp, L, gx, gy, acc);
       }
     }
-    __syncthreads();
-    ps.tile_block += (size_t)ps.tiles_x * ps.tiles_y;
-  }
-  if (in_image) {
-    accumulator[(size_t)gy * ps.width + gx] = acc;
-    if (FEAT) feature_sum[(size_t)gy * ps.width + gx] = feat, sample_count[(size_t)gy * ps.width + gx] = cnt;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
+    if ((it.pass & kReconLast) && in_image) {
+      accumulator[(size_t)gy * ps.width + gx] = acc;
+      if (FEAT) feature_sum[(size_t)gy * ps.width + gx] = feat, sample_count[(size_t)gy * ps.width + gx] = cnt;
+    }
+    if (++st == kReconStages) st = 0, use++;
   }
 }
 
