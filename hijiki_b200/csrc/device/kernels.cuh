@@ -1129,9 +1129,11 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
   bool in_image = false;
   for (uint32_t j = 0; j < n_items; j++) {
     mbar_wait(&full[st], use & 1u);
-    const ReconItem& it = items[st];  // (left in shared memory: fields are read where they are used)
-    const uint32_t pass = it.pass & 0x3FFFFFFFu;
-    if (it.pass & kReconFirst) {
+    const ReconItem& it = items[st];  // (left in shared memory: fields are read where they are used — all of them before
+                                      // this warp's arrival on empty[st] below, after which the producer may overwrite it)
+    const uint32_t item_flags = it.pass;
+    const uint32_t pass = item_flags & 0x3FFFFFFFu;
+    if (item_flags & kReconFirst) {
       wx = 4u * (((uint32_t)warp + j / n_passes) & 7u), tx_in = wx + ((uint32_t)lane & 3u);
       cidx = ((int)ty_in + R) * pitch + ((int)tx_in + R);
       gx = (uint32_t)it.tox + tx_in, gy = (uint32_t)it.toy + ty_in;
@@ -1223,7 +1225,7 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
-    if ((it.pass & kReconLast) && in_image) {
+    if ((item_flags & kReconLast) && in_image) {
       accumulator[(size_t)gy * ps.width + gx] = acc;
       if (FEAT) feature_sum[(size_t)gy * ps.width + gx] = feat, sample_count[(size_t)gy * ps.width + gx] = cnt;
     }

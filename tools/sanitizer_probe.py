@@ -40,3 +40,18 @@ rad = np.ones((72, 96, 4), np.float32); nrm = np.zeros((72, 96, 4), np.float32);
 ctx.frame_begin(96, 72)
 ctx.denoise_pass(rad, nrm, rad, hj.ImageBlockGenerator(96, 72, 64, 1).blocks(), hj.make_params())
 print("denoise ok", float(ctx.readback(normalise=False)[..., 3].mean()))
+# k_recon's persistent pipeline with many tiles per CTA (stage reuse, rotation of the warp rectangles), one pass and
+# several fused passes, edge tiles on every side (the frame is not a multiple of the tile or of the block)
+w, h = 2000, 1100
+rng = np.random.default_rng(2)
+rad = rng.random((h, w, 4), dtype=np.float32); rad[..., 3] = 1
+nrm = rng.standard_normal((h, w, 4)).astype(np.float32)
+ctx.frame_begin(w, h)
+ctx.denoise_upload(rad, nrm, hj.ImageBlockGenerator(w, h, 128, 1).blocks())
+ms = ctx.denoise_resident(hj.make_params(), 2)
+print("denoise resident ok", ms, float(ctx.readback(normalise=False)[..., 3].mean()), flush=True)
+ctx.set_option("feature_buffers", 1)
+blocks = hj.ImageBlockGenerator(640, 360, 128, 6).blocks()
+ctx.frame_begin(640, 360)
+st = ctx.render(blocks, hj.make_params(max_bounces=3))
+print("fused passes ok", st.n_rays, float(ctx.readback()[..., :3].mean()), flush=True)
