@@ -338,12 +338,16 @@ int launch_recon(HjkContext* c, const PassDev& ps_in, uint32_t n_passes, const f
   const dim3 block(kReconThreads);
   const uint32_t tiles_gx = (ps.width + kReconTileX - 1) / kReconTileX;
   const uint32_t n_tiles = tiles_gx * ((ps.height + kReconTileY - 1) / kReconTileY);
-  // persistent CTAs, as many as fit the device at once (k_recon's launch bound), each taking every grid-th tile
-  const dim3 grid(std::min<uint32_t>(n_tiles, (uint32_t)c->n_sms * HJK_RECON_MIN_BLOCKS));
+  // persistent CTAs, as many as are resident at once (registers and this radius' shared memory decide), each taking
+  // every grid-th tile
 #define HJK_RECON(A, RT, F)                                                                                         \
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
       HJK_CUDA(c, cudaFuncSetAttribute(k_recon<A, RT, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int per_sm = 0;                                                                                                 \
+    HJK_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_recon<A, RT, F>, kReconThreads, smem));    \
+    if (per_sm < 1) return c->fail(HJK_ERR_UNSUPPORTED, "k_recon does not fit an SM at recon_radius %d", ps.radius); \
+    const dim3 grid(std::min<uint32_t>(n_tiles, (uint32_t)(c->n_sms * per_sm)));                                    \
     k_recon<A, RT, F><<<grid, block, smem, c->stream>>>(ps, n_passes, tiles_gx, n_tiles, tm0, tm1, tm2, tm_acc, acc, \
                                                         c->feat(), c->cnt());                                       \
   } while (0)
