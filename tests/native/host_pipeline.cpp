@@ -87,9 +87,65 @@ struct FrameLayers {
 bool g_exact_ties = false;     // exact-tie mode of the harness (ht_set_exact)
 uint64_t g_unresolved = 0;
 
+// Work statistics of a tree (ht_work_stats): the same visiting order and acceptance rule as trav_run's default mode,
+// with the node steps and primitive tests counted — what the trace kernel's time is made of.
+bool g_count_work = false;
+uint64_t g_work[6];  // closest-hit rays, their node steps, their primitive tests; the same for any-hit rays
+template <int GUARD>
+void count_ray(const SceneDev& sc, TravState& s, HostStack& stack) {
+  uint64_t* w = g_work + ((s.slot >> 31) ? 3 : 0);
+  w[0]++;
+  for (;;) {
+    if (s.ng_y > 0x00FFFFFFu) {
+      const uint32_t hits_imask = s.ng_y;
+      const int bit = hi_bit(hits_imask);
+      s.ng_y &= ~(1u << bit);
+      if (s.ng_y > 0x00FFFFFFu) stack.push(s.ng_x, s.ng_y);
+      const uint32_t slot = ((uint32_t)bit - 24u) ^ (s.octinv4 & 0xFFu);
+      const uint32_t rel = (uint32_t)pop_count(hits_imask & ~(0xFFFFFFFFu << slot));
+      const f4* np = sc.nodes + (size_t)(s.ng_x + rel) * 5;
+      w[1]++;
+      const uint32_t hitmask = intersect_node<GUARD, false>(sc, s, np[0], np[1], np[2], np[3], np[4]);
+      s.ng_x = x::as_uint(np[1].x);
+      s.ng_y = (hitmask & 0xFF000000u) | (x::as_uint(np[0].w) >> 24);
+      s.tg_x = x::as_uint(np[1].y) & kWidePrimBaseMask;
+      s.tg_y = hitmask & 0x00FFFFFFu;
+    } else {
+      s.tg_x = s.ng_x, s.tg_y = s.ng_y;
+      s.ng_x = s.ng_y = 0;
+    }
+    while (s.tg_y) {
+      const int i = hi_bit(s.tg_y);
+      s.tg_y &= ~(1u << i);
+      const f4* pp = sc.prims + (size_t)(s.tg_x + (uint32_t)i) * HJK_PRIM_STRIDE;
+      float t, u, v;
+      w[2]++;
+      if (intersect_prim(sc, s, pp[0], pp[1], pp[2], pp[HJK_PRIM_STRIDE - 1], t, u, v)) {
+        if (s.slot >> 31) {
+          s.hit_id = (int32_t)x::as_uint(pp[0].w);
+          return;
+        }
+        if (closer_hit(s, t, x::as_uint(pp[0].w))) {
+          s.hit_id = (int32_t)x::as_uint(pp[0].w);
+          s.hit_t = t, s.hit_u = u, s.hit_v = v;
+          s.tmax = t;
+        }
+      }
+    }
+    if (s.ng_y <= 0x00FFFFFFu) {
+      if (stack.empty()) return;
+      stack.pop(s.ng_x, s.ng_y);
+    }
+  }
+}
+
 template <bool ANY_HIT, class Policy>
 bool run_ray(const SceneDev& sc, TravState& s, HostStack& st, float eps, const Policy& p) {
   s.slot = ANY_HIT ? 0x80000000u : 0u;
+  if (g_count_work) {
+    if (sc.num_spheres) count_ray<1>(sc, s, st); else count_ray<0>(sc, s, st);
+    return true;
+  }
   if (g_exact_ties) {
     const bool done = sc.num_spheres ? trav_run<true, true>(sc, s, st, eps, p, g_cands)
                                      : trav_run<false, true>(sc, s, st, eps, p, g_cands);
@@ -139,6 +195,22 @@ void* ht_create(const HjkScene* s, float pad_rel, char* err_out, int err_cap) {
   return h;
 }
 void ht_destroy(void* p) { delete (Harness*)p; }
+// node steps and primitive tests of the rays of a render (single-threaded): out6 = g_work
+int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm, float* accumulator,
+              float* layers_out, uint64_t* counts);
+int ht_work_stats(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const HjkParams* prm, uint64_t* out6) {
+  Harness* h = (Harness*)p;
+  const uint64_t W = blocks[0].original_dimension[0], H = blocks[0].original_dimension[1];
+  std::vector<float> acc(W * H * 4, 0.f);
+  HjkParams q = *prm;
+  q.flags |= HJK_RENDER_NO_RECON;
+  memset(g_work, 0, sizeof g_work);
+  g_count_work = true;
+  const int rc = ht_render(h, blocks, n_blocks, &q, acc.data(), nullptr, nullptr);
+  g_count_work = false;
+  memcpy(out6, g_work, sizeof g_work);
+  return rc;
+}
 void ht_set_exact(int on) {
   g_exact_ties = on != 0;
   g_unresolved = 0;
@@ -281,7 +353,6 @@ int ht_render(void* p, const HjkImageBlock* blocks, uint64_t n_blocks, const Hjk
       ps.tile_block = tile_block;
       ps.blocks = blocks;
       ps.weights = weights.data();
-    ps.taps = tap_lists.data();
       ps.taps = tap_lists.data();
       ps.radius = R;
       FrameLayers L{l0, l1, l2, W};

@@ -287,3 +287,21 @@ def test_non_unit_directions_match_the_reference_arithmetic(oracle, hosttest, re
     sph = hit & (ids_o < scene.info.num_spheres)
     assert sph.sum() > 100  # the sphere test itself was exercised with non-unit directions
     hosttest.ht_destroy(h)
+
+
+def test_work_statistics_count_the_rays_of_the_render(hosttest, cbox):
+    """tools/tree_work.py's counters (node steps / primitive tests per ray of the wide BVH) walk the same rays as the
+    render: ray counts equal, every ray takes at least the root step."""
+    h = _harness(hosttest, cbox)
+    blocks = _libs.generate_blocks(hosttest, 72, 40, 1, block_size=64)
+    prm = _libs.hjk_params(max_bounces=4)
+    acc = np.zeros((40, 72, 4), np.float32)
+    counts = np.zeros(3, np.uint64)
+    assert hosttest.ht_render(h, _libs.ptr(blocks), blocks.size, C.byref(prm), _libs.ptr(acc), None, _libs.ptr(counts)) == 0
+    hosttest.ht_work_stats.restype = C.c_int
+    hosttest.ht_work_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_abi.HjkParams), C.c_void_p]
+    work = np.zeros(6, np.uint64)
+    assert hosttest.ht_work_stats(h, _libs.ptr(blocks), blocks.size, C.byref(prm), _libs.ptr(work)) == 0
+    assert (work[0], work[3]) == (counts[1], counts[2])
+    assert work[1] >= work[0] and work[4] >= work[3] and work[2] > 0
+    hosttest.ht_destroy(h)
