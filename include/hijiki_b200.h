@@ -344,11 +344,12 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *   "bvh_broadcast"          several ranks: 1 = rank 0 builds and broadcasts the wide BVH (default), 0 = every rank builds
  *   "feature_buffers"        1 = sum the first-hit (normal, depth) per texel for hjk_read_features (default 0)
  *   "bvh_pad_rel_e9"         outward pad of primitive boxes, in 1e-9 of the scene extent (default 10000)
- *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default 20; an idle
- *                            warp always refills, so 0 is valid)
+ *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default -1 = by scene: 20,
+ *                            24 for trees that hold only spheres; an idle warp always refills, so 0 is valid)
  *   "coop_trace"             1 = k_trace_coop (default): a warp pools the primitive tests of its leaves and
  *                            spreads them over all 32 lanes when that is cheaper; 0 = per-lane k_trace
- *   "coop_batch_cost"        assumed instructions per pooled batch of 32 tests (default 180; 0 = always pool)
+ *   "coop_batch_cost"        assumed instructions per pooled batch of 32 tests (default -1 = by scene: 180, 260 for
+ *                            trees that hold only spheres; 0 = always pool)
  *   "postpone_lanes"         per-lane k_trace: postpone primitive tests that fewer lanes than this would run
  *                            (default 8)
  *   "shade_sort"             1 = counting-sort the hits of a shading tile by material so a warp shades one material,

@@ -455,7 +455,7 @@ def test_trace_kernel_variants_match_oracle(gpu_ctx, kind, max_bounces, use_bvh,
         acc_g = gpu_ctx.readback(normalise=False)
     finally:
         gpu_ctx.set_option("coop_trace", 1)
-        gpu_ctx.set_option("coop_batch_cost", 180)
+        gpu_ctx.set_option("coop_batch_cost", -1)
     acc_o, ost = _oracle_render(compiled, blocks, max_bounces, bs, use_bvh)
     diff = (acc_o.view(np.uint32) != acc_g.view(np.uint32)).any(axis=2)
     print(f"coop={coop}/{batch_cost} {kind}: texels differing {int(diff.sum())}; rays {st.n_extension_rays}+{st.n_shadow_rays} vs "
@@ -513,7 +513,7 @@ def test_default_mode_is_order_independent(gpu_ctx, kind, max_bounces):
             counts.append((st.n_paths, st.n_extension_rays, st.n_shadow_rays))
     finally:
         gpu_ctx.set_option("coop_trace", 1)
-        gpu_ctx.set_option("coop_batch_cost", 180)
+        gpu_ctx.set_option("coop_batch_cost", -1)
         gpu_ctx.set_option("wave_paths", 64 << 20)
     assert len(set(counts)) == 1, counts
     for f in frames[1:]:
@@ -579,7 +579,7 @@ def test_fetch_threshold_extremes_terminate_and_match(gpu_ctx, threshold):
         gpu_ctx.render(blocks, hj.make_params(max_bounces=12))
         got = gpu_ctx.readback(normalise=False)
     finally:
-        gpu_ctx.set_option("fetch_threshold", 20)
+        gpu_ctx.set_option("fetch_threshold", -1)
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
     assert gpu_ctx.get_info("stack_overflows") == 0
 
