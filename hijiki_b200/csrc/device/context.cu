@@ -470,8 +470,12 @@ int render_blocks(HjkContext* c, const HjkImageBlock* blocks, const HjkImageBloc
   // 512-sphere lattice) want fuller warps before a refill and a higher bar for pooling — a sphere test is half a
   // triangle test, so the pooling overhead weighs more: 1958 -> 1984 (cost 260) / 1990 (threshold 24) Mrays/s at 64
   // bounces; on cbox 20 / 24 and 180 / 240 measure the same within 0.3 %.
+  // A tree far larger than the L2 (the 10 M-triangle terrain: 560 MB) also wants the fuller warps: its node fetches are
+  // DRAM round trips, and more rays in flight hide them: 2254 -> 2293 Mrays/s (cbox: 29.65 -> 29.71 ms, so not there).
   const bool sphere_tree = c->bvh_all_guarded;
-  w.fetch_threshold = c->fetch_threshold >= 0 ? (uint32_t)c->fetch_threshold : (sphere_tree ? 24u : (uint32_t)kFetchThreshold);
+  const bool large_tree = c->n_nodes * sizeof(WideNode) + c->n_prims * sizeof(WidePrim) > (size_t)64 << 20;
+  w.fetch_threshold =
+      c->fetch_threshold >= 0 ? (uint32_t)c->fetch_threshold : (sphere_tree || large_tree ? 24u : (uint32_t)kFetchThreshold);
   // a postponed primitive group takes a second stack entry on its level: only trees of at most kMaxStack / 2 levels
   // (8^16 leaves) leave room for that, deeper ones are walked without postponing
   w.postpone_lanes = c->lane_postpones ? c->postpone_lanes : 0u;

@@ -345,7 +345,7 @@ HJK_API int hjk_set_profiling(HjkContext* ctx, int enabled); /* per-stage CUDA-e
  *   "feature_buffers"        1 = sum the first-hit (normal, depth) per texel for hjk_read_features (default 0)
  *   "bvh_pad_rel_e9"         outward pad of primitive boxes, in 1e-9 of the scene extent (default 10000)
  *   "fetch_threshold"        refill a traversal warp when fewer lanes than this are busy (default -1 = by scene: 20,
- *                            24 for trees that hold only spheres; an idle warp always refills, so 0 is valid)
+ *                            24 for trees that hold only spheres or exceed 64 MB; an idle warp always refills, so 0 is valid)
  *   "coop_trace"             1 = k_trace_coop (default): a warp pools the primitive tests of its leaves and
  *                            spreads them over all 32 lanes when that is cheaper; 0 = per-lane k_trace
  *   "coop_batch_cost"        assumed instructions per pooled batch of 32 tests (default -1 = by scene: 180, 260 for
