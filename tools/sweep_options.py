@@ -22,7 +22,7 @@ def run(label):
 run('default')
 for ft in (0,12,16,24,28,32):
     ctx.set_option('fetch_threshold',ft); run(f'fetch_threshold={ft}')
-ctx.set_option('fetch_threshold',20)
+ctx.set_option('fetch_threshold',-1)
 for pl in (0,4,12,16,20):
     ctx.set_option('postpone_lanes',pl); run(f'postpone_lanes={pl}')
 ctx.set_option('postpone_lanes',8)
