@@ -728,3 +728,28 @@ def test_asynchronous_readback(gpu_ctx):
     gpu_ctx.readback_wait()
     for k in range(2):
         assert np.array_equal(host[k].numpy().view(np.uint32), want[k].view(np.uint32))
+
+
+def test_reconstruction_pipeline_many_tiles_per_cta(gpu_ctx):
+    """k_recon's persistent pipeline with a dozen tiles per CTA (stage reuse, rectangles rotating over the warps), a frame
+    that is a multiple of neither the tile nor the block: five passes folded by one launch (the accumulator texel stays
+    in a register across them) against one launch per pass (it travels through the stage every time) — same bits, in
+    the accumulator and in the feature sums."""
+    compiled = _compiled("cbox")
+    gpu_ctx.scene_upload(compiled)
+    w, h, spp = 1610, 907, 5
+    blocks = hj.ImageBlockGenerator(w, h, 128, spp).blocks()
+    outs = []
+    gpu_ctx.set_option("feature_buffers", 1)
+    try:
+        for wave in (64 << 20, w * h):
+            gpu_ctx.set_option("wave_paths", wave)
+            gpu_ctx.frame_begin(w, h)
+            gpu_ctx.render(blocks, hj.make_params(max_bounces=2))
+            outs.append((gpu_ctx.readback(normalise=False), gpu_ctx.read_features()))
+    finally:
+        gpu_ctx.set_option("feature_buffers", 0)
+        gpu_ctx.set_option("wave_paths", 4 << 20)
+    assert np.isfinite(outs[0][0]).all() and outs[0][0][..., 3].min() > 0
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
