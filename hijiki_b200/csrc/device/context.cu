@@ -328,7 +328,7 @@ int launch_recon(HjkContext* c, const PassDev& ps_in, uint32_t n_passes, const f
   ps.one = 1.0f;
   const uint32_t layer_stride = recon_layer_stride(ps.radius);  // float4 elements, a multiple of 128 bytes
   const uint32_t stages = kReconStages;
-  const size_t smem = ((size_t)layer_stride * (l2 ? 3 : 2) + kReconConsumers) * sizeof(f4) * stages;
+  const size_t smem = (((size_t)layer_stride * (l2 ? 3 : 2) + kReconConsumers) * stages + (size_t)kReconSlots * kReconConsumers) * sizeof(f4);
   CUtensorMap tm0, tm1, tm2, tm_acc;
   int rc;
   if ((rc = recon_tensor_map(c, &tm0, l0, ps.width, ps.height, n_passes, ps.radius))) return rc;

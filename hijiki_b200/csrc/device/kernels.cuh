@@ -1025,6 +1025,15 @@ constexpr int kReconThreads = kReconConsumers + 32;
 HJK_HD uint32_t recon_layer_stride(int radius) {
   return ((uint32_t)(recon_smem_pitch(radius) * (kReconTileY + 2 * radius)) + 1u + 7u) & ~7u;
 }
+// Launches that fold several passes keep kReconSlots tiles of a CTA in flight at once, their items interleaved
+// (T0 p0, T1 p0, T2 p0, T3 p0, T0 p1, ...): the passes of ONE tile are a dependency chain through the accumulator, and
+// on a block edge the chain of the slow rectangle (3 times the work, the same warp for all the tile's passes) would
+// gate the CTA — interleaved, four different warps carry the slow rectangles of four tiles.  The accumulator texels of
+// a tile in flight live in shared memory (one 32 x 8 slot per tile, read and written by the one thread that owns the
+// texel), where the TMA engine delivers them on the tile's first pass.  More slots than stages, so that a slot's
+// previous tile is done by the time its next one is issued.
+constexpr uint32_t kReconSlots = 4;
+static_assert(kReconSlots > kReconStages, "a slot is reissued only after its previous tile left the pipeline");
 struct alignas(16) ReconItem {
   int32_t tox, toy;      // image coordinate of the tile's first texel
   int32_t cb;            // the block the whole tile lies in (block grid a multiple of the tile), else -1
@@ -1033,6 +1042,8 @@ struct alignas(16) ReconItem {
   uint32_t bdx, bdy;     //   dimension
   int32_t btx, bty;      //   position in the block grid
   uint32_t n_taps;       //   and length of its tap list
+  uint32_t slot, rot;    // accumulator slot of the tile (launches of several passes); the tile's number in the CTA's
+                         // sequence (rotates the rectangles over the warps)
 };
 constexpr uint32_t kReconFirst = 0x40000000u, kReconLast = 0x80000000u;
 // FEAT: also sum the texel's own first-hit features over the passes (feature_sum += (normal, depth),
@@ -1064,6 +1075,9 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
   const uint32_t n_items = my_tiles * n_passes;
   const size_t pass_tiles = (size_t)ps.tiles_x * ps.tiles_y;
   const bool aligned = RT >= 0 && ps.tile_w % kReconTileX == 0 && ps.tile_h % kReconTileY == 0;
+  // several passes (and no feature sums, which stay in registers): kReconSlots tiles in flight, accumulators in the slots
+  const uint32_t G = !FEAT && n_passes > 1 ? kReconSlots : 1u;
+  f4* const slots = smem + (size_t)kReconStages * stage_stride;  // [kReconSlots][32 x 8]
 
   if (warp == kReconConsumers / 32) {  // ---------------------------------------------------------------- producer
     // 32 items at a time: every lane derives one item's description (two dependent global loads: all in flight at
@@ -1072,7 +1086,12 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
     uint32_t st = 0, use = 0;
     for (uint32_t base = 0; base < n_items; base += 32u) {
       const uint32_t j = base + (uint32_t)lane;
-      const uint32_t tile = blockIdx.x + (j / n_passes) * gridDim.x, pass = j % n_passes;
+      // item j: groups of G tiles, inside a group pass-major
+      const uint32_t group = j / (G * n_passes), r = j - group * G * n_passes;
+      const uint32_t g_n = my_tiles - group * G < G ? my_tiles - group * G : G;  // (j >= n_items: never used)
+      const uint32_t pass = g_n ? r / g_n : 0u, g = g_n ? r % g_n : 0u;
+      const uint32_t seq = group * G + g;  // the tile's number in this CTA's sequence
+      const uint32_t tile = blockIdx.x + seq * gridDim.x;
       // tiles are numbered column by column: the tiles c, c + gridDim.x, ... of a CTA then fall on every position
       // inside a block (row-major, with 4 tiles per block row and a grid that is a multiple of 4, half of the CTAs
       // would get nothing but tiles on a block's left or right edge: 20 % more work than the others)
@@ -1083,6 +1102,7 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
       it.tox = (int32_t)(tbx * kReconTileX), it.toy = (int32_t)(tby * kReconTileY);
       it.pass = pass | (pass == 0 ? kReconFirst : 0u) | (last ? kReconLast : 0u);
       it.cb = -1, it.box = it.boy = 0, it.bdx = it.bdy = 0, it.btx = it.bty = 0, it.n_taps = 0;
+      it.slot = g, it.rot = seq;
       if (aligned && j < n_items) {
         it.btx = (int32_t)(tbx * kReconTileX / ps.tile_w), it.bty = (int32_t)(tby * kReconTileY / ps.tile_h);
         it.cb = ps.tile_block[(size_t)pass * pass_tiles + (size_t)it.bty * ps.tiles_x + it.btx];
@@ -1102,7 +1122,8 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
           tma_load_box3(dst, &tm0, &full[st], 4 * x0, y0, (int)pass);
           tma_load_box3(dst + layer_stride, &tm1, &full[st], 4 * x0, y0, (int)pass);
           if (HAS_ALBEDO) tma_load_box3(dst + 2 * layer_stride, &tm2, &full[st], 4 * x0, y0, (int)pass);
-          if (pass == 0) tma_load_box3(dst + NL * layer_stride, &tm_acc, &full[st], 4 * it.tox, it.toy, 0);
+          if (pass == 0)  // the tile's accumulator texels: into its slot, or (one tile at a time) into the stage
+            tma_load_box3(G > 1u ? slots + (size_t)g * kReconConsumers : dst + NL * layer_stride, &tm_acc, &full[st], 4 * it.tox, it.toy, 0);
           items[st] = it;
           // the stage's one arrival (release: the description is visible with it)
           mbar_expect_tx(&full[st], tx_bytes + (pass == 0 ? (uint32_t)kReconConsumers * 16u : 0u));
@@ -1133,11 +1154,14 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
                                       // this warp's arrival on empty[st] below, after which the producer may overwrite it)
     const uint32_t item_flags = it.pass;
     const uint32_t pass = item_flags & 0x3FFFFFFFu;
-    if (item_flags & kReconFirst) {
-      wx = 4u * (((uint32_t)warp + j / n_passes) & 7u), tx_in = wx + ((uint32_t)lane & 3u);
-      cidx = ((int)ty_in + R) * pitch + ((int)tx_in + R);
-      gx = (uint32_t)it.tox + tx_in, gy = (uint32_t)it.toy + ty_in;
-      in_image = gx < ps.width && gy < ps.height;
+    wx = 4u * (((uint32_t)warp + it.rot) & 7u), tx_in = wx + ((uint32_t)lane & 3u);
+    cidx = ((int)ty_in + R) * pitch + ((int)tx_in + R);
+    gx = (uint32_t)it.tox + tx_in, gy = (uint32_t)it.toy + ty_in;
+    in_image = gx < ps.width && gy < ps.height;
+    f4* const my_slot = slots + (size_t)it.slot * kReconConsumers + ty_in * kReconTileX + tx_in;
+    if (G > 1u) {
+      acc = *my_slot;  // delivered by the TMA engine on the tile's first pass, else this thread's own sum so far
+    } else if (item_flags & kReconFirst) {
       acc = smem[(size_t)st * stage_stride + NL * layer_stride + ty_in * kReconTileX + tx_in];  // came with the stage
       if (FEAT && in_image) feat = feature_sum[(size_t)gy * ps.width + gx], cnt = sample_count[(size_t)gy * ps.width + gx];
     }
@@ -1222,6 +1246,11 @@ __global__ void __launch_bounds__(kReconThreads, HJK_RECON_MIN_BLOCKS)
         pp.tile_block = tile_block;
         acc = reconstruct_pixel<HAS_ALBEDO>(pp, L, gx, gy, acc);
       }
+    }
+    if (G > 1u && !(item_flags & kReconLast)) {
+      *my_slot = acc;
+      // the slot's next tile arrives through the async proxy: order this generic-proxy write before it
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
