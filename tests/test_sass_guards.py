@@ -53,3 +53,20 @@ def test_packed_products_of_k_recon_are_not_contracted():
                 for k in range(1, width):
                     last_writer[dst + k] = op
     assert sums >= 8, f"only {sums} packed accumulations found: has the kernel changed?"
+
+
+@pytest.mark.parametrize("fn", ["k_trace_coopILi0E", "7k_traceILi0ELb0E"])
+def test_trace_kernels_have_no_local_memory(fn):
+    """The traversal stack lives in shared memory and the sphere-free trace kernels fit their registers: a spill here
+    once cost a third of k_trace_coop through one unrelated statement (profiles/README.md, r02d)."""
+    ops = _sass(fn)
+    local = [op for op, _ in ops if op.startswith(("LDL", "STL"))]
+    assert not local, f"{fn}: {len(local)} local-memory instructions"
+
+
+def test_reconstruction_uses_the_tma_engine_and_packed_pairs():
+    ops = [op for op, _ in _sass("k_reconILb0ELi2ELb0")]
+    assert sum(op.startswith("UTMALDG") for op in ops) == 3  # layer 0, layer 1, the accumulator tile
+    assert any(op.startswith("SYNCS") for op in ops)         # mbarrier
+    assert sum(op.startswith("FFMA2") for op in ops) >= 20 and sum(op.startswith("FMUL2") for op in ops) >= 20
+    assert not [op for op in ops if op.startswith(("LDL", "STL"))]
